@@ -1,0 +1,205 @@
+/*
+ * das_b200.h - C ABI of the B200-native active-selection scoring library (libdas_b200.so).
+ *
+ * This is the drop-in boundary for the scoring hot path of
+ * nihalsid/deep-active-semantic-segmentation.  The reference has no FFI layer of its own: its
+ * boundary is the Python method surface of active_selection/*.py.  The Python mirror of that
+ * surface lives in deep_active_semantic_segmentation_b200/active_selection/ and calls ONLY
+ * the functions declared here (via ctypes; see INTEGRATION.md for the binding stub).  Each entry
+ * point cites the reference code whose body it replaces (paths relative to the reference tree).
+ *
+ * Conventions
+ *  - plain C: pointers + sizes, no torch / C++ types.  All data pointers are DEVICE pointers
+ *    (sm_100a, HBM) unless a comment says "host".  Tensors are contiguous, row-major, NCHW.
+ *  - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).  No entry point
+ *    synchronises the host; all work is enqueued on `stream`.
+ *  - return value: DAS_OK (0) or a negative das_status; das_strerror() names it;
+ *    das_last_cuda_error() returns the cudaError_t behind DAS_ERR_CUDA.
+ *  - the caller owns every buffer; state / workspace sizes come from the *_bytes() queries.
+ *  - thread-compatible, not thread-safe: one host thread per state / workspace.
+ *  - there is NO CPU fallback anywhere behind this ABI.
+ */
+#ifndef DAS_B200_H
+#define DAS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DAS_ABI_VERSION 1
+
+typedef enum das_status {
+    DAS_OK = 0,
+    DAS_ERR_INVALID_ARG = -1,   /* NULL pointer, non-positive size, pass index out of range ... */
+    DAS_ERR_UNSUPPORTED = -2,   /* e.g. more than DAS_MAX_CLASSES classes, k > DAS_TOPK_MAX_K   */
+    DAS_ERR_CUDA = -3,          /* a CUDA runtime call failed; see das_last_cuda_error()         */
+    DAS_ERR_MISALIGNED = -4     /* a pointer violates the documented alignment                   */
+} das_status;
+
+const char* das_strerror(int status);
+int das_abi_version(void);
+int das_last_cuda_error(void);
+/* number of kernels this library has launched since load (bench.py's "gpu_launches") */
+uint64_t das_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------
+ * Monte-Carlo uncertainty reduction  (K1 accumulate + K2 finalize)
+ *
+ * Replaces the bodies of
+ *   ActiveSelectionMCDropout._get_vote_entropy_for_batch      active_selection/mc_dropout.py:30-80
+ *   ActiveSelectionMCNoise._get_vote_entropy_for_batch_with_* active_selection/mc_noise.py:21-44,62-84,86-114
+ *   ActiveSelectionCEAL._get_entropies / get_least_*          active_selection/ceal.py:19-126   (T = 1)
+ * and the per-image `torch.mean(...).cpu().item()` pooling (mc_dropout.py:189, mc_noise.py:56,
+ * ceal.py:59,95,123).
+ * ------------------------------------------------------------------------------------------ */
+
+#define DAS_MAX_CLASSES 32      /* register-resident class vector; votes are uint8            */
+#define DAS_MAX_PASSES 255      /* vote histogram counters are 8 bit                          */
+#define DAS_MAX_PASS_GROUP 32   /* passes consumed by one das_mc_accumulate launch            */
+
+enum {
+    DAS_MC_VOTES = 1,  /* keep the per-pass argmax votes   -> vote entropy (reference-pinned)   */
+    DAS_MC_PROBS = 2   /* keep running sum of softmax probabilities and of per-pass entropies   */
+                       /* -> predictive entropy, BALD, confidence, margin, expected entropy     */
+};
+
+/* order of the per-image scores written by das_mc_finalize */
+enum {
+    DAS_SCORE_VOTE_ENTROPY = 0,
+    DAS_SCORE_PRED_ENTROPY = 1,
+    DAS_SCORE_BALD = 2,
+    DAS_SCORE_CONFIDENCE = 3,
+    DAS_SCORE_MARGIN = 4,
+    DAS_SCORE_EXPECTED_ENTROPY = 5,
+    DAS_N_SCORES = 6
+};
+
+typedef struct das_mc_desc {
+    int32_t B;      /* images in the batch                                   */
+    int32_t C;      /* classes, 2..DAS_MAX_CLASSES                           */
+    int32_t H, W;   /* pixels                                                */
+    int32_t T_cap;  /* passes the state can hold, 1..DAS_MAX_PASSES          */
+    int32_t flags;  /* DAS_MC_VOTES | DAS_MC_PROBS                           */
+} das_mc_desc;
+
+/* Size of the caller-allocated state for `desc` (256-byte aligned device buffer). Layout:
+ * sum_p f32 [B,C,H,W] | sum_entropy f32 [B,H,W] | votes u8 [B,T_cap,H,W] | block partials. */
+int das_mc_state_bytes(const das_mc_desc* desc, size_t* bytes);
+
+/* Optional: zero the state. das_mc_accumulate(pass_begin = 0) initialises it anyway. */
+int das_mc_reset(const das_mc_desc* desc, void* state, void* stream);
+
+/* K1.  Consume `n_passes` (1..DAS_MAX_PASS_GROUP) Monte-Carlo passes in ONE launch.
+ * pass_logits: HOST array of n_passes DEVICE pointers, each f32 [B,C,H,W] logits of one stochastic
+ * forward (the value of `model(image_batch)`, mc_dropout.py:40).  Every logit is read exactly once;
+ * per pixel the kernel takes the first-max argmax (the vote), the max-subtracted softmax and its
+ * entropy, and adds them to the running state.  Passes pass_begin .. pass_begin+n_passes-1 are
+ * recorded; pass_begin == 0 (re)initialises the state.  n_passes == 1 is the pure streaming form;
+ * a larger group trades resident logits for fewer state round trips. */
+int das_mc_accumulate(const das_mc_desc* desc, void* state, const float* const* pass_logits,
+                      int n_passes, int pass_begin, void* stream);
+
+/* K2.  Turn the state after T passes into per-pixel maps and per-image scores.
+ * labels: f32 [B,H,W] or NULL; a pixel is valid iff 0 <= label < C (mc_dropout.py:45).  Invalid
+ *   pixels get 0 in the entropy-type maps (mc_dropout.py:49, ceal.py:119) and 1 in confidence /
+ *   margin (ceal.py:39,91).
+ * maps (each f32 [B,H,W] or NULL = not wanted):
+ *   vote_entropy   -sum_c p_c log2(p_c + 1e-12), p_c = votes_c / T         mc_dropout.py:46-48
+ *   pred_entropy   same formula on p_bar = mean_t softmax(x_t)               ceal.py:116-118 when T = 1
+ *   bald           pred_entropy - mean_t entropy(softmax(x_t))               (composed)
+ *   confidence     max_c p_bar                                               ceal.py:36
+ *   margin         largest - second largest p_bar                            ceal.py:84-90
+ * weak_labels: u8 [B,H,W] or NULL: vote of pass 0, 255 where invalid         ceal.py:157-163
+ * image_scores: f32 [B, DAS_N_SCORES] or NULL: mean over ALL H*W pixels of each map (a score whose
+ *   accumulator is not in desc->flags is written as NaN).
+ * Scores are reduced in a fixed order (deterministic, independent of how a pool is sharded). */
+int das_mc_finalize(const das_mc_desc* desc, void* state, const float* labels, int T,
+                    float* vote_entropy, float* pred_entropy, float* bald, float* confidence,
+                    float* margin, uint8_t* weak_labels, float* image_scores, void* stream);
+
+/* Device pointer to the recorded votes, u8 [B,T_cap,H,W] (test / debugging aid). */
+int das_mc_votes_ptr(const das_mc_desc* desc, void* state, uint8_t** votes);
+
+/* ------------------------------------------------------------------------------------------
+ * Region scoring
+ * ------------------------------------------------------------------------------------------ */
+
+/* ActiveSelectionMCDropout.suppress_labeled_entropy (mc_dropout.py:110-121):
+ * zero maps[i, r:r+h, c:c+w] for each of the n records (i, r, c, h, w) in `rects` (device, int32). */
+int das_suppress_rects(float* maps, int B, int H, int W, const int32_t* rects, int n, void* stream);
+
+/* a += b elementwise (combined noise + dropout vote entropy, mc_noise.py:141,165) */
+int das_add_maps(float* a, const float* b, size_t n, void* stream);
+
+/* Stride-1 'valid' RxR box sum, the conv2d-with-ones of mc_dropout.py:148-149:
+ * out[b,r,c] = sum_{i<R,j<R} maps[b,r+i,c+j], out is f32 [B,H-R+1,W-R+1].  Sums are formed in
+ * fp64 sliding windows and rounded once.  minmax: device f32[2] = {min,max}; it is COMBINED with the
+ * values already there (initialise with das_minmax_init), so a pool can be processed in batches
+ * (mc_dropout.py:152-153).  workspace: das_box_sum_workspace_bytes(). */
+int das_box_sum_workspace_bytes(int B, int H, int W, int R, size_t* bytes);
+int das_minmax_init(float* minmax, void* stream);
+int das_box_sum(const float* maps, int B, int H, int W, int R, float* out, float* minmax,
+                void* workspace, void* stream);
+
+/* x = (x + (-min)) * (1 / (max - min)) in float32, exactly as mc_dropout.py:154-155. */
+int das_minmax_normalise(float* score_maps, size_t n, const float* minmax, void* stream);
+
+/* Per-image greedy NMS pick sequences - the image-local part of
+ * ActiveSelectionMCDropout.square_nms (mc_dropout.py:82-108).  For each of the N images (one CTA
+ * each): repeat { first flat argmax (r,c); record; zero [r-R,r+R) x [c-R,c+R) } while picks < kmax
+ * and (it is the first pick or the map max >= stop).  MUTATES score_maps like the reference.
+ * cand_score f32 [N,kmax], cand_rc int32 [N,kmax,2], cand_count int32 [N].
+ * The global selection is the (score desc, flat index asc) merge of these sequences with the
+ * reference's stop rule - see active_selection/mc_dropout.py in the Python mirror. */
+int das_nms_sequences(float* score_maps, int N, int H2, int W2, int R, int kmax, float stop,
+                      float* cand_score, int32_t* cand_rc, int32_t* cand_count, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Ranking  (K3)
+ * Replaces `sorted(zip(scores, images), key=score, reverse=...)[:k]`
+ * (mc_dropout.py:195, ceal.py:69,97,130, mc_noise.py:59,128,147): a STABLE sort - equal scores keep
+ * input order - realised as a block radix select + sort on the composite key (score, position).
+ * ids: int64 [n] payload or NULL (then the position itself).  k is clamped to n.
+ * ------------------------------------------------------------------------------------------ */
+#define DAS_TOPK_MAX_K 4096
+int das_topk_workspace_bytes(int n, int k, size_t* bytes);
+int das_topk(const float* scores, const int64_t* ids, int n, int k, int descending,
+             float* out_scores, int64_t* out_ids, void* workspace, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Core-set k-center greedy  (K4)
+ * Replaces ActiveSelectionCoreSet._updated_distances / _select_batch (core_set.py:17-38):
+ * sklearn float64 euclidean distances + numpy argmax / minimum.
+ * feats: f32 [N,D] (the reference stores float32 network outputs widened to float64,
+ * core_set.py:50,63, so float32 holds the same values exactly).  Distances are accumulated in
+ * fp64 from exact float32 differences.  Rows [row_begin,row_end) are this rank's shard.
+ * ------------------------------------------------------------------------------------------ */
+
+/* min_d2[i - row_begin] = min_l ||f_i - f_centers[l]||^2 (fp64) for the L initial centres
+ * (core_set.py:19,32-36); also writes the packed argmax key of the shard to *key:
+ * (float64 bits of max min_d2 are order preserving since d2 >= 0) key = max over rows of
+ * pack(min_d2[i], i) with ties -> lowest i (np.argmax, core_set.py:22). */
+int das_kcenter_init(const float* feats, int N, int D, int row_begin, int row_end,
+                     const int32_t* centers, int L, double* min_d2, unsigned long long* key2,
+                     void* stream);
+
+/* One greedy step: centre = the row index held in *centre_idx (device int32); for every shard row
+ * min_d2 = min(min_d2, ||f_i - f_centre||^2) (core_set.py:26,37-38) and the new shard argmax is
+ * written to key2[0] (bits of the max), key2[1] (row index). */
+int das_kcenter_step(const float* feats, int N, int D, int row_begin, int row_end,
+                     const int32_t* centre_idx, double* min_d2, unsigned long long* key2,
+                     void* stream);
+
+/* Whole single-GPU greedy loop, no host round trip per step: picks int32 [K], min_d f64 [N]
+ * (final euclidean min-distances, i.e. sqrt).  workspace: das_kcenter_workspace_bytes(). */
+int das_kcenter_workspace_bytes(int N, int D, size_t* bytes);
+int das_kcenter_greedy(const float* feats, int N, int D, const int32_t* centers, int L, int K,
+                       int32_t* picks, double* min_d, void* workspace, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DAS_B200_H */

@@ -1,0 +1,298 @@
+"""TEST INFRASTRUCTURE - generates tests/golden/*.npz by running the reference's own selector
+classes (unmodified, on CPU, through oracle/ref_shim.py) on seeded synthetic inputs.
+
+Run in the build container only (needs /root/reference):
+    python -m oracle.gen_golden            # all fixtures
+    python -m oracle.gen_golden mc_small   # one fixture
+
+Inputs are regenerated at test time from (seed, shape) by
+deep_active_semantic_segmentation_b200/synth.py, so only the reference's OUTPUTS (and an
+input checksum) are stored; the two NMS PNG fixtures of the reference's own test
+(active_selection/tests.py:213-231) are stored as uint8 arrays.
+"""
+from __future__ import annotations
+
+import hashlib
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+sys.path.insert(0, ROOT)
+
+from deep_active_semantic_segmentation_b200 import synth  # noqa: E402
+from oracle import ref_shim  # noqa: E402
+
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def checksum(a: np.ndarray) -> str:
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()[:16]
+
+
+def versions():
+    import sklearn
+    import torch
+
+    return np.array([f"torch={torch.__version__}", f"numpy={np.__version__}", f"sklearn={sklearn.__version__}"])
+
+
+class SortedCapture:
+    """Replaces the builtin `sorted` inside a reference module so that the (score, path)
+    pairs the selector ranks can be recorded (the selectors only return the chosen paths)."""
+
+    def __init__(self):
+        self.calls = []
+
+    def __call__(self, iterable, key=None, reverse=False):
+        items = list(iterable)
+        self.calls.append(([float(x[0]) for x in items], reverse))
+        return sorted(items, key=key, reverse=reverse)
+
+
+def paths_to_idx(paths):
+    return np.array([int(p) for p in paths], dtype=np.int64)
+
+
+def regions_to_array(regions: dict, N: int):
+    rows = []
+    for i in range(N):
+        for (r, c, h, w) in regions.get(str(i), []):
+            rows.append((i, r, c, h, w))
+    return np.array(rows, dtype=np.int64).reshape(-1, 5)
+
+
+def make_pool(seed, N, T_total, C, H, W, block):
+    gs = list(range(N))
+    logits = synth.pool_logits(seed, gs, T_total, C, H, W, block)
+    labels = synth.pool_labels(seed, gs, H, W, C, block)
+    return ref_shim.SyntheticPool(logits, labels)
+
+
+# --------------------------------------------------------------------------------------
+
+def gen_mc(name, seed, N, T, C, H, W, block, k, batch_size):
+    """MC-dropout vote entropy (maps + image ranking) and the three CEAL scorers."""
+    ref = ref_shim.load_reference()
+    torch = ref.torch
+    ref.constants.MC_STEPS = T
+    pool = make_pool(seed, N, T, C, H, W, block)
+    paths = [str(i) for i in range(N)]
+    crop = H if H == W else -1
+
+    sel = ref.active_selection.get_active_selection_class("variance", C, pool, crop, batch_size)
+    cap = SortedCapture()
+    ref.mc_dropout.sorted = cap
+    chosen = sel.get_vote_entropy_for_images(ref_shim.make_replay_model(pool), paths, k)
+    del ref.mc_dropout.sorted
+    ve_scores = np.array(cap.calls[0][0], dtype=np.float32)
+
+    # per-pixel maps of the first batch, straight from _get_vote_entropy_for_batch
+    nb = min(batch_size, N)
+    ds = ref_shim.SyntheticPathsDataset(pool, paths[:nb], crop, include_labels=True)
+    image_batch = torch.stack([ds[i]["image"] for i in range(nb)])
+    label_batch = torch.stack([ds[i]["label"] for i in range(nb)])
+    maps = sel._get_vote_entropy_for_batch(ref_shim.make_replay_model(pool), image_batch, label_batch)
+    ve_maps = np.stack([m.numpy() for m in maps]).astype(np.float32)
+
+    ceal = ref.active_selection.get_active_selection_class("ceal_entropy", C, pool, crop, batch_size)
+    ent_sel, ent = ceal.get_maximum_entropy_samples(ref_shim.make_replay_model(pool), paths, k)
+    cap = SortedCapture()
+    ref.ceal.sorted = cap
+    conf_sel = ceal.get_least_confident_samples(ref_shim.make_replay_model(pool), paths, k)
+    marg_sel = ceal.get_least_margin_samples(ref_shim.make_replay_model(pool), paths, k)
+    del ref.ceal.sorted
+    conf_scores = np.array(cap.calls[0][0], dtype=np.float32)
+    marg_scores = np.array(cap.calls[1][0], dtype=np.float32)
+    weak = ceal.get_weakly_labeled_data(ref_shim.make_replay_model(pool), paths, float(np.median(ent)), entropies=list(ent))
+
+    np.savez_compressed(
+        os.path.join(GOLDEN, name + ".npz"),
+        meta=np.array([seed, N, T, C, H, W, block, k, batch_size], dtype=np.int64),
+        versions=versions(),
+        logits_sha=np.array(checksum(pool.logits)), labels_sha=np.array(checksum(pool.labels)),
+        ve_scores=ve_scores, ve_selected=paths_to_idx(chosen), ve_maps=ve_maps,
+        ceal_entropy=np.array(ent, dtype=np.float32), ceal_entropy_selected=paths_to_idx(ent_sel),
+        ceal_conf=conf_scores, ceal_conf_selected=paths_to_idx(conf_sel),
+        ceal_margin=marg_scores, ceal_margin_selected=paths_to_idx(marg_sel),
+        weak_idx=paths_to_idx(list(weak.keys())),
+        weak_labels=np.stack([weak[p] for p in weak]).astype(np.uint8) if weak else np.zeros((0, H, W), np.uint8),
+        weak_threshold=np.float64(np.median(ent)),
+    )
+    print(f"[golden] {name}: ve_scores[:4]={ve_scores[:4]} selected={paths_to_idx(chosen)}")
+
+
+def gen_region(name, seed, N, T, C, S, block, R, selection_size, batch_size):
+    """create_region_maps of mc_dropout (square crop S), with labelled-region suppression."""
+    ref = ref_shim.load_reference()
+    ref.constants.MC_STEPS = T
+    pool = make_pool(seed, N, T, C, S, S, block)
+    paths = [str(i) for i in range(N)]
+    rng = np.random.default_rng(seed + 1)
+    existing = []
+    for i in range(N):
+        if i % 3 == 0:
+            existing.append([])
+        elif i % 3 == 1:
+            r0, c0 = (int(v) for v in rng.integers(0, S - R, size=2))
+            existing.append([(r0, c0, R, R)])
+        else:
+            existing.append([(int(rng.integers(0, S - R)), int(rng.integers(0, S - R)), R, R) for _ in range(2)])
+    if N > 4:
+        existing[4] = [(0, 0, S, S)]  # fully labelled image (region_cityscapes.py:26)
+
+    recorded = {}
+    orig = ref.mc_dropout.ActiveSelectionMCDropout.square_nms
+
+    def recording_nms(score_maps, region_size, max_selection_count):
+        recorded["norm"] = score_maps.numpy().copy()
+        recorded["K"] = float(max_selection_count)
+        return orig(score_maps, region_size, max_selection_count)
+
+    ref.mc_dropout.ActiveSelectionMCDropout.square_nms = staticmethod(recording_nms)
+    try:
+        sel = ref.active_selection.get_active_selection_class("variance", C, pool, S, batch_size)
+        regions, count = sel.create_region_maps(ref_shim.make_replay_model(pool), paths, existing, R, selection_size)
+    finally:
+        ref.mc_dropout.ActiveSelectionMCDropout.square_nms = staticmethod(orig)
+
+    ex_rows = np.array([(i, *rc) for i, lst in enumerate(existing) for rc in lst], dtype=np.int64).reshape(-1, 5)
+    np.savez_compressed(
+        os.path.join(GOLDEN, name + ".npz"),
+        meta=np.array([seed, N, T, C, S, block, R, selection_size, batch_size], dtype=np.int64),
+        versions=versions(), logits_sha=np.array(checksum(pool.logits)),
+        existing=ex_rows, regions=regions_to_array(regions, N), count=np.int64(count),
+        norm_maps=recorded["norm"].astype(np.float32), K=np.float64(recorded["K"]),
+    )
+    print(f"[golden] {name}: {count} regions over {len(regions)} images, K={recorded['K']:.2f}")
+
+
+def gen_noise(name, seed, N, T, C, S, block, R, k, batch_size):
+    """mc_noise.py: input-noise / feature-noise / noise+dropout image scores and its region maps."""
+    ref = ref_shim.load_reference()
+    ref.constants.MC_STEPS = T
+    pool = make_pool(seed, N, 2 * T, C, S, S, block)   # combined variants consume 2T forwards per batch
+    paths = [str(i) for i in range(N)]
+    sel = ref.active_selection.get_active_selection_class("noise_variance", C, pool, S, batch_size)
+    cap = SortedCapture()
+    ref.mc_noise.sorted = cap
+    np.random.seed(0)
+    s_in = sel.get_vote_entropy_for_images_with_input_noise(ref_shim.make_replay_model(pool), paths, k)
+    s_ft = sel.get_vote_entropy_for_images_with_feature_noise(ref_shim.make_replay_model(pool), paths, k)
+    s_cb = sel.get_vote_entropy_for_batch_with_noise_and_vote_entropy(ref_shim.make_replay_model(pool), paths, k)
+    del ref.mc_noise.sorted
+    existing = [[] for _ in range(N)]
+    existing[1] = [(3, 5, R, R)]
+    regions, count = sel.create_region_maps(ref_shim.make_replay_model(pool), paths, existing, R, 1)
+    np.savez_compressed(
+        os.path.join(GOLDEN, name + ".npz"),
+        meta=np.array([seed, N, T, C, S, block, R, k, batch_size], dtype=np.int64),
+        versions=versions(), logits_sha=np.array(checksum(pool.logits)),
+        input_noise_scores=np.array(cap.calls[0][0], np.float32), input_noise_selected=paths_to_idx(s_in),
+        feature_noise_scores=np.array(cap.calls[1][0], np.float32), feature_noise_selected=paths_to_idx(s_ft),
+        combined_scores=np.array(cap.calls[2][0], np.float32), combined_selected=paths_to_idx(s_cb),
+        existing=np.array([(1, 3, 5, R, R)], dtype=np.int64),
+        regions=regions_to_array(regions, N), count=np.int64(count),
+    )
+    print(f"[golden] {name}: combined_selected={paths_to_idx(s_cb)} regions={count}")
+
+
+def gen_kcenter_toy():
+    """reference active_selection/tests.py:557-562."""
+    ref = ref_shim.load_reference()
+    sel = ref.core_set.ActiveSelectionCoreSet(None, None, None)
+    feats = np.array([[1, 1], [2, 2], [2, 4], [3, 3], [4, 2], [4, 5], [5, 4], [6, 2], [7, 6]])
+    picks = sel._select_batch(feats, [6], 5)
+    np.savez_compressed(os.path.join(GOLDEN, "kcenter_toy.npz"), features=feats, selected=np.array([6]),
+                        picks=np.array(picks, dtype=np.int64), versions=versions())
+    print(f"[golden] kcenter_toy: {picks}")
+
+
+def gen_coreset(name, seed, N, D, L, K):
+    """_select_batch on float64 copies of float32 features (core_set.py:50,17-30)."""
+    ref = ref_shim.load_reference()
+    sel = ref.core_set.ActiveSelectionCoreSet(None, None, None)
+    feats32 = synth.coreset_features(seed, N, D)
+    picks = sel._select_batch(feats32.astype(np.float64), list(range(L)), K)
+    # final min-distances, recomputed with the reference's own update rule
+    md = sel._updated_distances(list(range(L)) + [int(p) for p in picks], feats32.astype(np.float64), None)
+    np.savez_compressed(os.path.join(GOLDEN, name + ".npz"),
+                        meta=np.array([seed, N, D, L, K], dtype=np.int64), versions=versions(),
+                        features_sha=np.array(checksum(feats32)),
+                        picks=np.array(picks, dtype=np.int64), min_dist=md[:, 0].astype(np.float64))
+    print(f"[golden] {name}: picks[:8]={picks[:8]} max min-dist={md.max():.6f}")
+
+
+def gen_coreset_e2e(name, seed, N, L, K, batch_size):
+    """get_k_center_greedy_selections with the ENet geometry (128ch @64x64 -> 32x32/16 avg-pool
+    -> 1152-d; core_set.py:47-49) through the replay model."""
+    ref = ref_shim.load_reference()
+    rng = np.random.Generator(np.random.Philox(key=[seed, 77]))
+    feats = rng.standard_normal(size=(N, 128, 64, 64), dtype=np.float32)
+    feats += (rng.integers(0, 4, size=(N, 1, 1, 1)) * 0.5).astype(np.float32)
+    pool = ref_shim.SyntheticPool(np.zeros((N, 1, 2, 64, 64), np.float32), None, feats)
+    sel = ref.active_selection.get_active_selection_class("coreset", 2, pool, 64, batch_size)
+    already = [str(i) for i in range(L)]
+    cand = [str(i) for i in range(L, N)]
+    chosen = sel.get_k_center_greedy_selections(K, ref_shim.make_replay_model(pool, "enet"), cand, already)
+    np.savez_compressed(os.path.join(GOLDEN, name + ".npz"),
+                        meta=np.array([seed, N, L, K, batch_size], dtype=np.int64), versions=versions(),
+                        features_sha=np.array(checksum(feats)), chosen=paths_to_idx(chosen))
+    print(f"[golden] {name}: chosen={paths_to_idx(chosen)}")
+
+
+def gen_nms_png():
+    """reference active_selection/tests.py:213-231 on resources/images/nms_{0,1}.png (CPU conv2d,
+    the two real maps only, min-max with -min)."""
+    from PIL import Image
+
+    ref = ref_shim.load_reference()
+    torch = ref.torch
+    imgs = [np.asarray(Image.open(os.path.join(ref_shim.REFERENCE_ROOT, "resources", "images", f"nms_{i}.png")))
+            for i in range(2)]
+    R = 127
+    w = torch.ones(1, 1, R, R)
+    maps = torch.stack([torch.nn.functional.conv2d(torch.from_numpy(im.astype(np.float32) / 256)[None, None], w)[0, 0]
+                        for im in imgs])
+    raw = maps.numpy().copy()
+    mn, mx = maps.min(), maps.max()
+    maps.add_(-mn).mul_(1.0 / (mx - mn))
+    norm = maps.numpy().copy()
+    regions, count = ref.mc_dropout.ActiveSelectionMCDropout.square_nms(maps, R, (512 * 512) // (R * R))
+    rows = np.array([(i, *rc) for i, lst in enumerate(regions) for rc in lst], dtype=np.int64)
+    np.savez_compressed(os.path.join(GOLDEN, "nms_png.npz"), images=np.stack(imgs).astype(np.uint8),
+                        R=np.int64(R), K=np.int64((512 * 512) // (R * R)), raw_max=np.float32(raw.max()),
+                        raw_maps=raw.astype(np.float32), norm_maps=norm.astype(np.float32),
+                        regions=rows, count=np.int64(count), versions=versions())
+    print(f"[golden] nms_png: count={count} regions={rows.tolist()}")
+
+
+FIXTURES = {
+    # odd H*W (alignment-peeling path), Pascal class count
+    "mc_small": lambda: gen_mc("mc_small", synth.DEFAULT_SEED, N=6, T=5, C=21, H=65, W=65, block=8, k=3, batch_size=4),
+    # H*W % 4 == 0 (128-bit path), Cityscapes class count and T, rectangular
+    "mc_aligned": lambda: gen_mc("mc_aligned", synth.DEFAULT_SEED + 1, N=5, T=20, C=19, H=32, W=64, block=8, k=2, batch_size=2),
+    # BASELINE config 1 shape: 16 x 513x513, C=21, T=5
+    "mc_config1": lambda: gen_mc("mc_config1", synth.DEFAULT_SEED + 2, N=16, T=5, C=21, H=513, W=513, block=32, k=8, batch_size=4),
+    "region_small": lambda: gen_region("region_small", synth.DEFAULT_SEED + 3, N=6, T=5, C=21, S=65, block=8, R=17, selection_size=1, batch_size=4),
+    "region_mid": lambda: gen_region("region_mid", synth.DEFAULT_SEED + 4, N=5, T=8, C=19, S=129, block=16, R=33, selection_size=2, batch_size=2),
+    "noise_small": lambda: gen_noise("noise_small", synth.DEFAULT_SEED + 5, N=6, T=4, C=21, S=65, block=8, R=17, k=3, batch_size=4),
+    "kcenter_toy": gen_kcenter_toy,
+    "coreset_small": lambda: gen_coreset("coreset_small", synth.DEFAULT_SEED + 6, N=400, D=96, L=10, K=40),
+    "coreset_mid": lambda: gen_coreset("coreset_mid", synth.DEFAULT_SEED + 7, N=1500, D=2736, L=50, K=60),
+    "coreset_e2e": lambda: gen_coreset_e2e("coreset_e2e", synth.DEFAULT_SEED + 8, N=14, L=4, K=5, batch_size=4),
+    "nms_png": gen_nms_png,
+}
+
+
+def main(argv):
+    os.makedirs(GOLDEN, exist_ok=True)
+    names = argv or list(FIXTURES)
+    for n in names:
+        FIXTURES[n]()
+
+
+if __name__ == "__main__":
+    main(sys.argv[1:])

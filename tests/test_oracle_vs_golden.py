@@ -1,0 +1,182 @@
+"""CPU: the restatement (oracle/restate.py) must reproduce what the reference's own code
+produced (tests/golden/*.npz, made by oracle/gen_golden.py) - this is what pins the oracle."""
+import numpy as np
+import pytest
+
+from oracle import restate as R
+from tests import golden_util as G
+
+RTOL = 1e-5   # north_star tolerance (relative, float32)
+ATOL = 1e-6   # absolute floor for per-pixel maps / means that can be ~0
+
+
+def _mc_case(name, n=None):
+    g = G.load(name)
+    seed, N, T, C, H, W, block, k, bs = (int(v) for v in g["meta"])
+    logits, labels = G.pool_from_meta(seed, N, T, C, H, W, block, g["logits_sha"], n)
+    return g, (seed, N, T, C, H, W, block, k, bs), logits, labels
+
+
+@pytest.mark.parametrize("name,n", [("mc_small", None), ("mc_aligned", None), ("mc_config1", 4)])
+def test_vote_entropy_and_ceal_match_reference(name, n):
+    g, (seed, N, T, C, H, W, block, k, bs), logits, labels = _mc_case(name, n)
+    n = N if n is None else n
+    sc = {key: [] for key in R.SCORE_NAMES}
+    ceal = {"pred_entropy": [], "confidence": [], "margin": []}
+    for i in range(n):
+        maps = R.mc_maps(logits[i], labels[i], C)
+        if i < g["ve_maps"].shape[0]:
+            np.testing.assert_allclose(maps["vote_entropy"], g["ve_maps"][i], rtol=RTOL, atol=ATOL)
+        s = R.image_scores(maps)
+        for key in sc:
+            sc[key].append(s[key])
+        single = R.image_scores(R.mc_maps(logits[i, :1], labels[i], C))   # CEAL = the T=1 case
+        for key in ceal:
+            ceal[key].append(single[key])
+    np.testing.assert_allclose(sc["vote_entropy"], g["ve_scores"][:n], rtol=RTOL, atol=1e-7)
+    np.testing.assert_allclose(ceal["pred_entropy"], g["ceal_entropy"][:n], rtol=RTOL, atol=1e-7)
+    np.testing.assert_allclose(ceal["confidence"], g["ceal_conf"][:n], rtol=RTOL, atol=1e-7)
+    np.testing.assert_allclose(ceal["margin"], g["ceal_margin"][:n], rtol=RTOL, atol=1e-7)
+    if n == N:
+        assert R.rank_topk(sc["vote_entropy"], k, True) == g["ve_selected"].tolist()
+        assert R.rank_topk(ceal["pred_entropy"], k, True) == g["ceal_entropy_selected"].tolist()
+        assert R.rank_topk(ceal["confidence"], k, False) == g["ceal_conf_selected"].tolist()
+        assert R.rank_topk(ceal["margin"], k, False) == g["ceal_margin_selected"].tolist()
+        # weak labels = argmax of the deterministic pass, 255 where invalid (ceal.py:157-163)
+        for j, i in enumerate(g["weak_idx"].tolist()):
+            wl = R.votes_from_logits(logits[i, 0]).copy()
+            wl[~R.valid_mask(labels[i], C)] = 255
+            np.testing.assert_array_equal(wl, g["weak_labels"][j])
+
+
+def test_golden_rankings_are_consistent_with_golden_scores():
+    # the stored selections are the stable sort of the stored scores (pins rank_topk's tie rule)
+    for name in ("mc_small", "mc_aligned", "mc_config1"):
+        g = G.load(name)
+        k = int(g["meta"][7])
+        assert R.rank_topk(g["ve_scores"].tolist(), k, True) == g["ve_selected"].tolist()
+        assert R.rank_topk(g["ceal_conf"].tolist(), k, False) == g["ceal_conf_selected"].tolist()
+
+
+def test_rank_topk_is_stable_on_ties():
+    s = [0.5, 0.25, 0.5, 0.75, 0.25, 0.5]
+    assert R.rank_topk(s, 4, True) == [3, 0, 2, 5]
+    assert R.rank_topk(s, 3, False) == [1, 4, 0]
+    assert R.rank_topk(s, 10, True) == [3, 0, 2, 5, 1, 4]
+    assert R.rank_topk([], 3, True) == []
+
+
+@pytest.mark.parametrize("name", ["region_small", "region_mid"])
+def test_region_selection_matches_reference(name):
+    g = G.load(name)
+    seed, N, T, C, S, block, Rg, sel_size, bs = (int(v) for v in g["meta"])
+    logits, labels = G.pool_from_meta(seed, N, T, C, S, S, block, g["logits_sha"])
+    existing = G.regions_from_rows(g["existing"], N)
+    ve = [R.mc_maps(logits[i], labels[i], C)["vote_entropy"] for i in range(N)]
+    (regions, count), norm = R.region_selection(ve, existing, Rg, sel_size, S)
+    np.testing.assert_allclose(norm, g["norm_maps"], rtol=RTOL, atol=ATOL)
+    assert count == int(g["count"])
+    assert regions == G.regions_from_rows(g["regions"], N)
+    # sharded formulation (per-image sequences + merge) == the sequential global loop
+    K = float(g["K"])
+    seqs = [R.nms_sequence_single(norm[i].copy(), Rg, int(np.ceil(K))) for i in range(N)]
+    merged, mcount = R.merge_nms_sequences(seqs, Rg, K, norm.shape[1], norm.shape[2])
+    assert (merged, mcount) == (regions, count)
+
+
+def test_nms_png_fixture():
+    """reference active_selection/tests.py:213-231 (the reference's own data-free NMS case)."""
+    g = G.load("nms_png")
+    Rg, K = int(g["R"]), int(g["K"])
+    raw = np.stack([R.box_sum(im.astype(np.float32) / 256, Rg) for im in g["images"]])
+    np.testing.assert_array_equal(raw, g["raw_maps"])       # k/256 sums are exact in float32
+    assert raw.max() == np.float32(8860.890625)
+    norm = R.minmax_normalise(raw)
+    np.testing.assert_array_equal(norm, g["norm_maps"])
+    regions, count = R.square_nms(norm.copy(), Rg, K)
+    assert count == 10 == int(g["count"])
+    assert regions == G.regions_from_rows(g["regions"], 2)
+    assert regions[0] == [(18, 72, 127, 127), (275, 294, 127, 127), (114, 199, 127, 127), (362, 0, 127, 127), (241, 166, 127, 127)]
+    seqs = [R.nms_sequence_single(norm[i].copy(), Rg, K) for i in range(2)]
+    assert R.merge_nms_sequences(seqs, Rg, K, 386, 386) == (regions, count)
+
+
+def test_nms_degenerate_all_below_threshold():
+    # the first pick is unconditional, then the loop stops (mc_dropout.py:91-106)
+    m = np.full((3, 5, 5), 0.001, dtype=np.float32)
+    ref_regions, ref_count = R.square_nms(m.copy(), 2, 4.0)
+    assert ref_count == 1 and ref_regions[0] == [(0, 0, 2, 2)]
+    seqs = [R.nms_sequence_single(m[i].copy(), 2, 4) for i in range(3)]
+    assert R.merge_nms_sequences(seqs, 2, 4.0, 5, 5) == (ref_regions, ref_count)
+
+
+def test_nms_merge_equals_sequential_on_random_pools():
+    rng = np.random.default_rng(5)
+    for trial in range(12):
+        N, H2, W2, Rg = int(rng.integers(1, 6)), int(rng.integers(6, 30)), int(rng.integers(6, 30)), int(rng.integers(2, 7))
+        m = rng.random((N, H2, W2)).astype(np.float32)
+        m[rng.random(m.shape) < 0.3] = 0
+        if trial % 3 == 0:
+            m = np.round(m, 1)       # many exact ties
+        K = float(rng.integers(1, 40)) + 0.5
+        ref = R.square_nms(m.copy(), Rg, K)
+        seqs = [R.nms_sequence_single(m[i].copy(), Rg, int(np.ceil(K))) for i in range(N)]
+        assert R.merge_nms_sequences(seqs, Rg, K, H2, W2) == ref
+
+
+def test_noise_fixture():
+    g = G.load("noise_small")
+    seed, N, T, C, S, block, Rg, k, bs = (int(v) for v in g["meta"])
+    logits, labels = G.pool_from_meta(seed, N, 2 * T, C, S, S, block, g["logits_sha"])
+    first = [R.mc_maps(logits[i, :T], labels[i], C)["vote_entropy"] for i in range(N)]
+    second = [R.mc_maps(logits[i, T:], labels[i], C)["vote_entropy"] for i in range(N)]
+    s_first = [float(np.float32(m.sum(dtype=np.float64)) / (S * S)) for m in first]
+    s_comb = [float(np.float32((a + b).sum(dtype=np.float64)) / (S * S)) for a, b in zip(first, second)]
+    # every mc_noise scorer starts a fresh replay model -> passes 0..T-1 (mc_noise.py:46-60,116-129)
+    np.testing.assert_allclose(s_first, g["input_noise_scores"], rtol=RTOL, atol=1e-7)
+    np.testing.assert_allclose(s_first, g["feature_noise_scores"], rtol=RTOL, atol=1e-7)
+    np.testing.assert_allclose(s_comb, g["combined_scores"], rtol=RTOL, atol=1e-7)   # mc_noise.py:141-143
+    assert R.rank_topk(s_comb, k, True) == g["combined_selected"].tolist()
+    existing = G.regions_from_rows(g["existing"], N)
+    (regions, count), _ = R.region_selection([a + b for a, b in zip(first, second)], existing, Rg, 1, S)
+    assert count == int(g["count"]) and regions == G.regions_from_rows(g["regions"], N)
+
+
+def test_kcenter_toy_fixture():
+    g = G.load("kcenter_toy")
+    picks, m = R.kcenter_greedy(g["features"], g["selected"].tolist(), 5)
+    assert picks == [0, 2, 8, 4, 7] == g["picks"].tolist()
+    assert abs(m.max() - 1.41421) < 1e-5
+
+
+@pytest.mark.parametrize("name", ["coreset_small", "coreset_mid"])
+def test_kcenter_matches_reference(name):
+    from deep_active_semantic_segmentation_b200 import synth
+
+    g = G.load(name)
+    seed, N, D, L, K = (int(v) for v in g["meta"])
+    feats = synth.coreset_features(seed, N, D)
+    assert G.sha(feats) == str(g["features_sha"])
+    picks, m = R.kcenter_greedy(feats, list(range(L)), K)
+    assert picks == g["picks"].tolist()
+    # d = sqrt(|x|^2+|y|^2-2x.y) cancels to ~1e-6 of noise where the true distance is 0
+    np.testing.assert_allclose(m, g["min_dist"], rtol=1e-9, atol=5e-6)
+
+
+def test_kcenter_asserts_on_reselection():
+    feats = np.zeros((4, 3), dtype=np.float32)     # all distances 0 -> argmax = 0, already selected
+    with pytest.raises(AssertionError):
+        R.kcenter_greedy(feats, [0], 1)
+
+
+def test_coreset_e2e_fixture():
+    g = G.load("coreset_e2e")
+    seed, N, L, K, bs = (int(v) for v in g["meta"])
+    rng = np.random.Generator(np.random.Philox(key=[seed, 77]))
+    feats = rng.standard_normal(size=(N, 128, 64, 64), dtype=np.float32)
+    feats += (rng.integers(0, 4, size=(N, 1, 1, 1)) * 0.5).astype(np.float32)
+    assert G.sha(feats) == str(g["features_sha"])
+    rows = np.stack([R.avg_pool_features(feats[i], 32) for i in range(N)])
+    assert rows.shape == (N, 1152)
+    picks, _ = R.kcenter_greedy(rows, list(range(L)), K)
+    assert picks == g["chosen"].tolist()      # combined = already + candidates -> index == path
