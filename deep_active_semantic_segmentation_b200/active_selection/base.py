@@ -1,0 +1,135 @@
+"""Shared machinery of the selector mirror (reference active_selection/base.py:1-6 + the loops that
+every selector repeats).  The scoring itself happens in libdas_b200.so through ..ops."""
+from __future__ import annotations
+
+import math
+import sys
+import types
+
+import torch
+from torch.utils.data import DataLoader
+
+from .. import constants as _own_constants
+from .. import dist, ops
+from .._lib import SCORE_INDEX, DasError
+
+# The reference selectors reach the data layer through the module attribute
+# `paths_dataset.PathsDataset` (mc_dropout.py:131, ceal.py:21, core_set.py:42).  The data layer is out
+# of scope here: by default the caller's own `dataloaders.dataset.paths_dataset` is used; tests and
+# bench.py assign `paths_dataset.PathsDataset = <synthetic dataset>`.
+paths_dataset = types.SimpleNamespace(PathsDataset=None)
+
+
+def _dataset_class():
+    if paths_dataset.PathsDataset is not None:
+        return paths_dataset.PathsDataset
+    try:
+        from dataloaders.dataset import paths_dataset as ref_paths_dataset  # the caller's data layer
+    except Exception as exc:  # pragma: no cover - depends on the embedding application
+        raise DasError("no PathsDataset available: run inside the reference tree or set "
+                       "deep_active_semantic_segmentation_b200.active_selection.base.paths_dataset.PathsDataset") from exc
+    return ref_paths_dataset.PathsDataset
+
+
+def mc_steps() -> int:
+    """`constants.MC_STEPS`, read at call time like the reference does (mc_dropout.py:37,39,47)."""
+    ref = sys.modules.get("constants")
+    if ref is not None and hasattr(ref, "MC_STEPS"):
+        return int(ref.MC_STEPS)
+    return int(_own_constants.MC_STEPS)
+
+
+def turn_on_dropout(model) -> None:
+    """Dropout2d -> train mode so forwards are stochastic (mc_dropout.py:175-178)."""
+    def _flip(m):
+        if type(m) == torch.nn.Dropout2d:
+            m.train()
+    model.apply(_flip)
+
+
+class ActiveSelectionBase:
+
+    def __init__(self, dataset_lmdb_env, crop_size, dataloader_batch_size):
+        self.crop_size = crop_size
+        self.dataloader_batch_size = dataloader_batch_size
+        self.env = dataset_lmdb_env
+        #: Monte-Carlo passes held back and consumed by ONE das_mc_accumulate launch (1 = pure streaming)
+        self.pass_group = 1
+        #: scores of the last pool pass, global image order (diagnostics / parity tests)
+        self.last_scores = None
+
+    # -- pool iteration ------------------------------------------------------------------------
+    def _shard(self, images):
+        W, rank = dist.world()
+        lo, hi = dist.shard_bounds(len(images), W, rank)
+        return lo, hi
+
+    def _loader(self, images, include_labels=True):
+        ds = _dataset_class()(self.env, images, self.crop_size, include_labels=include_labels)
+        return DataLoader(ds, batch_size=self.dataloader_batch_size, shuffle=False, num_workers=0)
+
+    # -- Monte-Carlo scoring of one batch --------------------------------------------------------
+    def _mc_batch(self, forward, image_batch, label_batch, T, votes, probs, maps=(), weak_labels=False):
+        """T calls of `forward(image_batch)` -> K1 accumulate (streaming) -> K2 finalize."""
+        B, _, H, W = image_batch.shape
+        state = None
+        pending = []
+        with torch.no_grad():
+            for step in range(T):
+                logits = forward(image_batch)
+                if state is None:
+                    state = ops.MCState(B, logits.shape[1], H, W, T, votes=votes, probs=probs, device=logits.device)
+                pending.append(logits)
+                if len(pending) >= self.pass_group or step == T - 1:
+                    state.accumulate(pending)
+                    pending = []
+        return state.finalize(label_batch, maps=maps, scores=True, weak_labels=weak_labels)
+
+    # -- ranking -----------------------------------------------------------------------------------
+    def _rank(self, local_scores, lo, images, k, descending):
+        """local_scores: f32 CUDA tensor for images[lo:lo+n].  Local K3 top-k, candidate all-gather,
+        stable global merge -> tuple of the first k paths (all ranks return the same tuple)."""
+        if len(images) == 0:
+            raise IndexError("list index out of range")   # the reference fails on zip(*[])[1] (mc_dropout.py:195)
+        n = local_scores.numel()
+        k_eff = max(0, min(int(k), len(images)))
+        if n and k_eff:
+            s, i = ops.topk(local_scores, min(k_eff, n), descending)
+        else:
+            s, i = local_scores[:0], torch.empty(0, dtype=torch.int64, device=local_scores.device)
+        cs, ci = dist.gather_candidates(s, i + lo, max(k_eff, 1))
+        _, ids = dist.merge_ranked(cs, ci, k_eff, descending)
+        return tuple(images[j] for j in ids)
+
+    def _all_scores(self, local_scores, n_total):
+        """Full score list in global order (list of python floats), gathered over ranks."""
+        W, _ = dist.world()
+        vals = local_scores.detach().cpu().tolist()
+        if W == 1:
+            return vals
+        out = []
+        for part in dist.gather_objects(vals):
+            out += part
+        assert len(out) == n_total
+        return out
+
+
+def region_tail(selector, score_maps, images, lo, region_size, selection_size):
+    """Everything after the per-image box sums of create_region_maps (mc_dropout.py:152-171):
+    pool min-max normalisation, image-local NMS sequences on the GPU, global merge, result dict."""
+    N_local, H2, W2 = score_maps.shape
+    H, W = H2 + region_size - 1, W2 + region_size - 1
+    base_sq = H * W   # == base_size**2 for the reference's square crops (mc_dropout.py:129,157)
+    num_requested = (selection_size * base_sq) / (region_size * region_size)
+    mm = dist.allreduce_minmax(selector._minmax)
+    ops.minmax_normalise(score_maps, mm)
+    kmax = max(1, min(math.ceil(num_requested), ops.nms_pick_bound(H2, W2, region_size)))
+    cs, rc, cnt = ops.nms_sequences(score_maps, region_size, kmax, 0.01)
+    cs, rc, cnt = cs.cpu(), rc.cpu(), cnt.cpu().tolist()
+    local = [[(cs[i, j].item(), int(rc[i, j, 0]), int(rc[i, j, 1])) for j in range(cnt[i])] for i in range(N_local)]
+    seqs = []
+    for part in dist.gather_objects(local):
+        seqs += part
+    regions, count = dist.merge_nms_sequences(seqs, region_size, num_requested, H2, W2)
+    new_regions = {images[i]: regions[i] for i in range(len(regions)) if regions[i]}
+    return new_regions, count

@@ -1,0 +1,111 @@
+"""Mirror of reference active_selection/core_set.py (ActiveSelectionCoreSet): k-center greedy over
+average-pooled decoder features.  Feature extraction stays in PyTorch on the device (no per-image
+D2H, core_set.py:63); distances / min-update / arg-max run in the K4 kernels (fp64 accumulation)."""
+from __future__ import annotations
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+from .. import dist, ops
+from .._lib import DasError
+from .base import ActiveSelectionBase
+
+_POOL = {"deeplab": (64, 64), "enet": (32, 32)}  # core_set.py:44-49
+
+
+class ActiveSelectionCoreSet(ActiveSelectionBase):
+
+    def __init__(self, dataset_lmdb_env, crop_size, dataloader_batch_size):
+        super(ActiveSelectionCoreSet, self).__init__(dataset_lmdb_env, crop_size, dataloader_batch_size)
+        self.last_min_distances = None
+
+    @staticmethod
+    def _as_device_features(features):
+        if isinstance(features, torch.Tensor):
+            f = features
+            if f.dtype != torch.float32:
+                if not torch.equal(f.to(torch.float32).to(f.dtype), f):
+                    raise DasError("core-set features must be exactly representable in float32")
+                f = f.to(torch.float32)
+            return f.cuda().contiguous()
+        a = np.asarray(features)
+        a32 = a.astype(np.float32)
+        if not np.array_equal(a32.astype(np.float64), a.astype(np.float64)):
+            raise DasError("core-set features must be exactly representable in float32 "
+                           "(the reference stores float32 network outputs, core_set.py:50,63)")
+        return torch.from_numpy(np.ascontiguousarray(a32)).cuda()
+
+    def _select_batch(self, features, selected_indices, N):
+        """features [n,D] (numpy / tensor), selected_indices list[int], N picks -> list[int] (core_set.py:17-30)."""
+        feats = self._as_device_features(features)
+        selected = [int(i) for i in selected_indices]
+        if len(selected) == 0:
+            raise ValueError("k-center needs at least one already selected row (core_set.py:19)")
+        W, rank = dist.world()
+        if W == 1:
+            picks, min_d = ops.kcenter_greedy(feats, selected, N)
+            picks = picks.cpu().tolist()
+        else:
+            picks, min_d = self._select_batch_sharded(feats, selected, N, W, rank)
+        self.last_min_distances = min_d
+        for ind in picks:
+            # "New examples should not be in already selected" (core_set.py:23-25)
+            assert ind not in selected
+        if min_d.numel():
+            print('Maximum distance from cluster centers is %0.5f' % float(min_d.max()))
+        return picks
+
+    def _select_batch_sharded(self, feats, selected, N, W, rank):
+        """Rows of min_d sharded over ranks, features replicated; one 16-byte exchange per step
+        (value bits, row index) - the arg-max all-reduce of SURVEY.md section 8(e)(iii)."""
+        import torch.distributed as td
+
+        n = feats.shape[0]
+        lo, hi = dist.shard_bounds(n, W, rank)
+        if hi <= lo:
+            raise DasError("this rank received an empty shard of the feature rows")
+        dev = feats.device
+        min_d2 = torch.empty(hi - lo, dtype=torch.float64, device=dev)
+        key = torch.zeros(2, dtype=torch.int64, device=dev)
+        centre = torch.zeros(1, dtype=torch.int32, device=dev)
+        cen = torch.as_tensor(selected, dtype=torch.int32, device=dev)
+        ops.kcenter_init(feats, lo, hi, cen, min_d2, key)
+        picks = []
+        keys = [torch.empty_like(key) for _ in range(W)]
+        for _ in range(N):
+            td.all_gather(keys, key)
+            allk = torch.stack(keys)                       # [W,2]: (fp64 bits of the shard max, row)
+            best = allk[:, 0].max()
+            row = torch.where(allk[:, 0] == best, allk[:, 1], torch.full_like(allk[:, 1], 2 ** 62)).min()
+            centre.copy_(row.to(torch.int32).reshape(1))
+            picks.append(row)
+            ops.kcenter_step(feats, lo, hi, centre, min_d2, key)
+        parts = [torch.empty(dist.shard_bounds(n, W, r)[1] - dist.shard_bounds(n, W, r)[0], dtype=torch.float64, device=dev)
+                 for r in range(W)]
+        td.all_gather(parts, min_d2)
+        return [int(p) for p in torch.stack(picks).cpu().tolist()] if picks else [], torch.cat(parts).sqrt()
+
+    def _pooled_features(self, model, combined_paths):
+        name = model.module.model_name
+        if name not in _POOL:
+            raise NotImplementedError(name)
+        ks = _POOL[name]
+        rows = []
+        model.eval()
+        model.module.set_return_features(True)
+        try:
+            with torch.no_grad():
+                for sample in self._loader(combined_paths, include_labels=False):
+                    _, fb = model(sample.cuda())
+                    fb = F.avg_pool2d(fb, ks, ks[0] // 2)
+                    rows.append(fb.reshape(fb.shape[0], -1).to(torch.float32))   # channel-major flatten (core_set.py:63)
+        finally:
+            model.module.set_return_features(False)
+        return torch.cat(rows).contiguous()
+
+    def get_k_center_greedy_selections(self, selection_size, model, candidate_image_batch, already_selected_image_batch):
+        combined_paths = already_selected_image_batch + candidate_image_batch
+        features = self._pooled_features(model, combined_paths)
+        selected_indices = self._select_batch(features, list(range(len(already_selected_image_batch))), selection_size)
+        return [combined_paths[i] for i in selected_indices]

@@ -1,0 +1,245 @@
+// K4: core-set k-center greedy (reference active_selection/core_set.py:17-38).
+//   min_d2[i] = min over centres of ||f_i - f_c||^2, accumulated in fp64 from float32 features widened
+//   exactly (the reference widens the same float32 network outputs to float64, core_set.py:50,63);
+//   pick = first argmax (np.argmax, core_set.py:22); update with the new centre (core_set.py:26,37-38).
+// One warp per feature row; a step streams the N x D feature matrix once (L2 resident for the
+// BASELINE size: 10k x 2048 x 4 B = 82 MB < 126 MB).  Every block leaves its best (value,row) in a small
+// table; the NEXT launch starts by reducing that table, so the greedy loop is a chain of launches with
+// no host round trip, no atomics and a deterministic tie rule.
+#include <math.h>
+
+#include "das_common.cuh"
+
+namespace das {
+
+constexpr int kKcThreads = 256;
+constexpr int kKcWarps = kKcThreads / 32;
+
+struct KcBest {
+    double v;
+    int idx;
+    int pad;
+};
+
+__device__ __forceinline__ bool kc_better(double v, int i, double bv, int bi) {
+    return v > bv || (v == bv && i < bi);  // larger distance, then lower row index
+}
+
+// squared distance between rows a and b (length D) by one warp, fp64 accumulation
+template <bool VEC4>
+__device__ __forceinline__ double warp_dist2(const float* __restrict__ a, const float* __restrict__ b, int D, int lane) {
+    double s0 = 0.0, s1 = 0.0;
+    if (VEC4) {
+        const float4* a4 = reinterpret_cast<const float4*>(a);
+        const float4* b4 = reinterpret_cast<const float4*>(b);
+        for (int i = lane; i < D / 4; i += 32) {
+            const float4 x = a4[i], y = b4[i];
+            const double d0 = (double)x.x - (double)y.x, d1 = (double)x.y - (double)y.y;
+            const double d2 = (double)x.z - (double)y.z, d3 = (double)x.w - (double)y.w;
+            s0 = fma(d0, d0, s0);
+            s1 = fma(d1, d1, s1);
+            s0 = fma(d2, d2, s0);
+            s1 = fma(d3, d3, s1);
+        }
+    } else {
+        for (int i = lane; i < D; i += 32) {
+            const double d = (double)a[i] - (double)b[i];
+            s0 = fma(d, d, s0);
+        }
+    }
+    return warp_sum(s0 + s1);
+}
+
+// MODE 0: init  - min over the L given centres              (core_set.py:19)
+// MODE 1: step  - centre index read from *centre_ptr        (multi-GPU: host all-reduced it)
+// MODE 2: chain - centre = argmax of the previous launch's block table; block 0 records the pick
+template <bool VEC4, int MODE>
+__global__ void __launch_bounds__(kKcThreads) kcenter_kernel(const float* __restrict__ feats, int D, int row_begin,
+                                                             int row_end, const int32_t* __restrict__ centres, int L,
+                                                             double* __restrict__ min_d2,
+                                                             const KcBest* __restrict__ prev_best, int n_prev,
+                                                             KcBest* __restrict__ next_best, int32_t* picks, int step) {
+    __shared__ double sv[kKcWarps];
+    __shared__ int si[kKcWarps];
+    __shared__ int centre_s;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+
+    int centre = -1;
+    if (MODE == 1) centre = centres[0];
+    if (MODE == 2) {
+        double bv = -1.0;
+        int bi = 0x7fffffff;
+        for (int i = tid; i < n_prev; i += kKcThreads) {
+            const KcBest q = prev_best[i];
+            if (q.idx >= 0 && kc_better(q.v, q.idx, bv, bi)) bv = q.v, bi = q.idx;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const double ov = __shfl_xor_sync(0xffffffffu, bv, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            if (kc_better(ov, oi, bv, bi)) bv = ov, bi = oi;
+        }
+        if (lane == 0) sv[wid] = bv, si[wid] = bi;
+        __syncthreads();
+        if (tid == 0) {
+            for (int w = 1; w < kKcWarps; ++w)
+                if (kc_better(sv[w], si[w], bv, bi)) bv = sv[w], bi = si[w];
+            centre_s = bi;
+            if (blockIdx.x == 0 && picks != nullptr) picks[step] = bi;
+        }
+        __syncthreads();
+        centre = centre_s;
+        __syncthreads();
+    }
+
+    double bv = -1.0;
+    int bi = -1;
+    for (int row = row_begin + blockIdx.x * kKcWarps + wid; row < row_end; row += gridDim.x * kKcWarps) {
+        const float* fr = feats + (size_t)row * D;
+        double m;
+        if (MODE == 0) {
+            m = INFINITY;
+            for (int l = 0; l < L; ++l) m = fmin(m, warp_dist2<VEC4>(fr, feats + (size_t)centres[l] * D, D, lane));
+        } else {
+            m = fmin(min_d2[row - row_begin], warp_dist2<VEC4>(fr, feats + (size_t)centre * D, D, lane));
+        }
+        if (lane == 0) min_d2[row - row_begin] = m;
+        if (bi < 0 || kc_better(m, row, bv, bi)) bv = m, bi = row;
+    }
+    if (lane == 0) sv[wid] = bv, si[wid] = bi;
+    __syncthreads();
+    if (tid == 0) {
+        for (int w = 1; w < kKcWarps; ++w)
+            if (si[w] >= 0 && (bi < 0 || kc_better(sv[w], si[w], bv, bi))) bv = sv[w], bi = si[w];
+        KcBest q;
+        q.v = bv, q.idx = bi, q.pad = 0;
+        next_best[blockIdx.x] = q;
+    }
+}
+
+// reduce a block table to the packed pair key2 = {fp64 bits of the max, row index}
+__global__ void kcenter_key_kernel(const KcBest* best, int n, unsigned long long* key2, int32_t* picks, int step) {
+    double bv = -1.0;
+    int bi = 0x7fffffff;
+    for (int i = 0; i < n; ++i)
+        if (best[i].idx >= 0 && kc_better(best[i].v, best[i].idx, bv, bi)) bv = best[i].v, bi = best[i].idx;
+    if (key2 != nullptr) {
+        key2[0] = (unsigned long long)__double_as_longlong(bv < 0.0 ? 0.0 : bv);
+        key2[1] = (unsigned long long)(unsigned int)bi;
+    }
+    if (picks != nullptr) picks[step] = bi;
+}
+
+__global__ void kcenter_sqrt_kernel(const double* d2, int n, double* d) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) d[i] = sqrt(d2[i]);
+}
+
+static int kc_grid(int rows) {
+    const int want = (rows + kKcWarps - 1) / kKcWarps;
+    const int cap = kNumSMs * 4;
+    return want < cap ? (want < 1 ? 1 : want) : cap;
+}
+static bool kc_vec4(const float* feats, int D) { return D % 4 == 0 && aligned16(feats); }
+
+struct KcWorkspace {
+    KcBest* best[2];
+    double* d2;
+};
+static KcWorkspace kc_carve(void* ws, int N) {
+    KcWorkspace w;
+    char* p = static_cast<char*>(ws);
+    const size_t tbl = align_up((size_t)kNumSMs * 4 * sizeof(KcBest), 256);
+    w.best[0] = reinterpret_cast<KcBest*>(p);
+    w.best[1] = reinterpret_cast<KcBest*>(p + tbl);
+    w.d2 = reinterpret_cast<double*>(p + 2 * tbl);
+    (void)N;
+    return w;
+}
+
+template <int MODE>
+static int kc_launch(bool v4, int grid, cudaStream_t st, const float* feats, int D, int rb, int re, const int32_t* centres,
+                     int L, double* min_d2, const KcBest* prev, int n_prev, KcBest* next, int32_t* picks, int step) {
+    if (v4)
+        DAS_LAUNCH((kcenter_kernel<true, MODE>), grid, kKcThreads, 0, st, feats, D, rb, re, centres, L, min_d2, prev,
+                   n_prev, next, picks, step);
+    else
+        DAS_LAUNCH((kcenter_kernel<false, MODE>), grid, kKcThreads, 0, st, feats, D, rb, re, centres, L, min_d2, prev,
+                   n_prev, next, picks, step);
+    DAS_CHECK_LAUNCH();
+    return DAS_OK;
+}
+
+}  // namespace das
+
+using namespace das;
+
+// scratch table for the step-wise (multi-GPU) entry points: one per process is enough because the
+// ABI is thread-compatible, not thread-safe.
+static KcBest* g_step_table = nullptr;
+static int ensure_step_table() {
+    if (g_step_table == nullptr) DAS_CUDA(cudaMalloc(&g_step_table, (size_t)kNumSMs * 4 * sizeof(KcBest)));
+    return DAS_OK;
+}
+
+extern "C" {
+
+int das_kcenter_init(const float* feats, int N, int D, int row_begin, int row_end, const int32_t* centers, int L,
+                     double* min_d2, unsigned long long* key2, void* stream) {
+    if (feats == nullptr || centers == nullptr || min_d2 == nullptr || key2 == nullptr) return DAS_ERR_INVALID_ARG;
+    if (N <= 0 || D <= 0 || L <= 0 || row_begin < 0 || row_end > N || row_begin >= row_end) return DAS_ERR_INVALID_ARG;
+    int rc = ensure_step_table();
+    if (rc != DAS_OK) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int grid = kc_grid(row_end - row_begin);
+    rc = kc_launch<0>(kc_vec4(feats, D), grid, st, feats, D, row_begin, row_end, centers, L, min_d2, nullptr, 0,
+                      g_step_table, nullptr, 0);
+    if (rc != DAS_OK) return rc;
+    DAS_LAUNCH(kcenter_key_kernel, 1, 1, 0, st, g_step_table, grid, key2, nullptr, 0);
+    DAS_CHECK_LAUNCH();
+    return DAS_OK;
+}
+
+int das_kcenter_step(const float* feats, int N, int D, int row_begin, int row_end, const int32_t* centre_idx,
+                     double* min_d2, unsigned long long* key2, void* stream) {
+    if (feats == nullptr || centre_idx == nullptr || min_d2 == nullptr || key2 == nullptr) return DAS_ERR_INVALID_ARG;
+    if (N <= 0 || D <= 0 || row_begin < 0 || row_end > N || row_begin >= row_end) return DAS_ERR_INVALID_ARG;
+    int rc = ensure_step_table();
+    if (rc != DAS_OK) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int grid = kc_grid(row_end - row_begin);
+    rc = kc_launch<1>(kc_vec4(feats, D), grid, st, feats, D, row_begin, row_end, centre_idx, 1, min_d2, nullptr, 0,
+                      g_step_table, nullptr, 0);
+    if (rc != DAS_OK) return rc;
+    DAS_LAUNCH(kcenter_key_kernel, 1, 1, 0, st, g_step_table, grid, key2, nullptr, 0);
+    DAS_CHECK_LAUNCH();
+    return DAS_OK;
+}
+
+int das_kcenter_workspace_bytes(int N, int D, size_t* bytes) {
+    if (bytes == nullptr || N <= 0 || D <= 0) return DAS_ERR_INVALID_ARG;
+    *bytes = 2 * align_up((size_t)kNumSMs * 4 * sizeof(KcBest), 256) + align_up((size_t)N * sizeof(double), 256);
+    return DAS_OK;
+}
+
+int das_kcenter_greedy(const float* feats, int N, int D, const int32_t* centers, int L, int K, int32_t* picks,
+                       double* min_d, void* workspace, void* stream) {
+    if (feats == nullptr || centers == nullptr || picks == nullptr || min_d == nullptr || workspace == nullptr)
+        return DAS_ERR_INVALID_ARG;
+    if (N <= 0 || D <= 0 || L <= 0 || K < 0) return DAS_ERR_INVALID_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    const KcWorkspace w = kc_carve(workspace, N);
+    const bool v4 = kc_vec4(feats, D);
+    const int grid = kc_grid(N);
+    int rc = kc_launch<0>(v4, grid, st, feats, D, 0, N, centers, L, w.d2, nullptr, 0, w.best[0], nullptr, 0);
+    if (rc != DAS_OK) return rc;
+    for (int s = 0; s < K; ++s) {
+        rc = kc_launch<2>(v4, grid, st, feats, D, 0, N, nullptr, 0, w.d2, w.best[s & 1], grid, w.best[(s + 1) & 1],
+                          picks, s);
+        if (rc != DAS_OK) return rc;
+    }
+    DAS_LAUNCH(kcenter_sqrt_kernel, kc_grid(N), kKcThreads, 0, st, w.d2, N, min_d);
+    DAS_CHECK_LAUNCH();
+    return DAS_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,205 @@
+// extern "C" entry points of the Monte-Carlo reduction (K1/K2): validation, state layout, dispatch.
+#include <math.h>
+
+#include "mc_kernels.cuh"
+
+namespace das {
+
+int g_last_cuda_error = 0;
+unsigned long long g_launch_count = 0;
+
+// class-count ranges compiled in separate translation units (see build.py)
+#define DAS_DECL_RANGE(LO, HI)                                                                         \
+    int dispatch_accumulate_##LO##_##HI(const McAccParams&, int, bool, int, cudaStream_t);             \
+    int dispatch_finalize_##LO##_##HI(const McFinParams&, int, bool, int, cudaStream_t);
+DAS_DECL_RANGE(2, 9)
+DAS_DECL_RANGE(10, 16)
+DAS_DECL_RANGE(17, 20)
+DAS_DECL_RANGE(21, 24)
+DAS_DECL_RANGE(25, 28)
+DAS_DECL_RANGE(29, 32)
+
+int dispatch_accumulate(const McAccParams& p, int B, bool v4, int f, cudaStream_t st) {
+    if (p.C <= 9) return dispatch_accumulate_2_9(p, B, v4, f, st);
+    if (p.C <= 16) return dispatch_accumulate_10_16(p, B, v4, f, st);
+    if (p.C <= 20) return dispatch_accumulate_17_20(p, B, v4, f, st);
+    if (p.C <= 24) return dispatch_accumulate_21_24(p, B, v4, f, st);
+    if (p.C <= 28) return dispatch_accumulate_25_28(p, B, v4, f, st);
+    return dispatch_accumulate_29_32(p, B, v4, f, st);
+}
+int dispatch_finalize(const McFinParams& p, int B, bool v4, int f, cudaStream_t st) {
+    if (p.C <= 9) return dispatch_finalize_2_9(p, B, v4, f, st);
+    if (p.C <= 16) return dispatch_finalize_10_16(p, B, v4, f, st);
+    if (p.C <= 20) return dispatch_finalize_17_20(p, B, v4, f, st);
+    if (p.C <= 24) return dispatch_finalize_21_24(p, B, v4, f, st);
+    if (p.C <= 28) return dispatch_finalize_25_28(p, B, v4, f, st);
+    return dispatch_finalize_29_32(p, B, v4, f, st);
+}
+
+int mc_validate(const das_mc_desc* d) {
+    if (d == nullptr) return DAS_ERR_INVALID_ARG;
+    if (d->B <= 0 || d->H <= 0 || d->W <= 0 || d->T_cap <= 0) return DAS_ERR_INVALID_ARG;
+    if ((d->flags & (DAS_MC_VOTES | DAS_MC_PROBS)) == 0 || (d->flags & ~(DAS_MC_VOTES | DAS_MC_PROBS)))
+        return DAS_ERR_INVALID_ARG;
+    if (d->C < 2) return DAS_ERR_INVALID_ARG;
+    if (d->C > DAS_MAX_CLASSES || d->T_cap > DAS_MAX_PASSES || d->B > 65535) return DAS_ERR_UNSUPPORTED;
+    return DAS_OK;
+}
+
+static bool use_vec4(const das_mc_desc& d) { return ((long long)d.H * d.W) % 4 == 0; }
+
+McLayout mc_layout(const das_mc_desc& d) {
+    McLayout L;
+    const size_t HW = (size_t)d.H * d.W;
+    const int vec = use_vec4(d) ? 4 : 1;
+    L.blocks_per_image = (int)((HW + (size_t)kFinalizeThreads * vec - 1) / ((size_t)kFinalizeThreads * vec));
+    size_t off = 0;
+    L.sum_p = off;
+    if (d.flags & DAS_MC_PROBS) off += align_up((size_t)d.B * d.C * HW * sizeof(float), 256);
+    L.sum_ent = off;
+    if (d.flags & DAS_MC_PROBS) off += align_up((size_t)d.B * HW * sizeof(float), 256);
+    L.votes = off;
+    if (d.flags & DAS_MC_VOTES) off += align_up((size_t)d.B * d.T_cap * HW, 256);
+    L.partials = off;
+    off += align_up((size_t)d.B * L.blocks_per_image * DAS_N_SCORES * sizeof(float), 256);
+    L.total = off;
+    return L;
+}
+
+// one warp per (image, score): fixed-order fp64 sum of the block partials -> mean over H*W
+__global__ void mc_reduce_partials_kernel(const float* partials, int blocks_per_image, long long HW, int flags,
+                                          float* image_scores) {
+    const int b = blockIdx.x;
+    const int k = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (k >= DAS_N_SCORES) return;
+    double s = 0.0;
+    for (int i = lane; i < blocks_per_image; i += 32)
+        s += (double)partials[((size_t)b * blocks_per_image + i) * DAS_N_SCORES + k];
+    s = warp_sum(s);
+    if (lane == 0) {
+        const bool have = (k == DAS_SCORE_VOTE_ENTROPY) ? (flags & DAS_MC_VOTES) : (flags & DAS_MC_PROBS);
+        image_scores[(size_t)b * DAS_N_SCORES + k] = have ? (float)(s / (double)HW) : __int_as_float(0x7fc00000);
+    }
+}
+
+}  // namespace das
+
+using namespace das;
+
+extern "C" {
+
+const char* das_strerror(int status) {
+    switch (status) {
+        case DAS_OK: return "ok";
+        case DAS_ERR_INVALID_ARG: return "invalid argument";
+        case DAS_ERR_UNSUPPORTED: return "unsupported size (see DAS_MAX_* in das_b200.h)";
+        case DAS_ERR_CUDA: return "CUDA runtime error (see das_last_cuda_error)";
+        case DAS_ERR_MISALIGNED: return "pointer not aligned as documented";
+        default: return "unknown das_status";
+    }
+}
+int das_abi_version(void) { return DAS_ABI_VERSION; }
+int das_last_cuda_error(void) { return g_last_cuda_error; }
+uint64_t das_launch_count(void) { return g_launch_count; }
+
+int das_mc_state_bytes(const das_mc_desc* desc, size_t* bytes) {
+    int rc = mc_validate(desc);
+    if (rc != DAS_OK) return rc;
+    if (bytes == nullptr) return DAS_ERR_INVALID_ARG;
+    *bytes = mc_layout(*desc).total;
+    return DAS_OK;
+}
+
+int das_mc_reset(const das_mc_desc* desc, void* state, void* stream) {
+    int rc = mc_validate(desc);
+    if (rc != DAS_OK) return rc;
+    if (state == nullptr) return DAS_ERR_INVALID_ARG;
+    DAS_CUDA(cudaMemsetAsync(state, 0, mc_layout(*desc).total, (cudaStream_t)stream));
+    return DAS_OK;
+}
+
+int das_mc_accumulate(const das_mc_desc* desc, void* state, const float* const* pass_logits, int n_passes,
+                      int pass_begin, void* stream) {
+    int rc = mc_validate(desc);
+    if (rc != DAS_OK) return rc;
+    if (state == nullptr || pass_logits == nullptr) return DAS_ERR_INVALID_ARG;
+    if (n_passes < 1 || pass_begin < 0 || pass_begin + n_passes > desc->T_cap) return DAS_ERR_INVALID_ARG;
+    if (n_passes > DAS_MAX_PASS_GROUP) return DAS_ERR_UNSUPPORTED;
+    const bool v4 = use_vec4(*desc);
+    if (!aligned16(state)) return DAS_ERR_MISALIGNED;
+    McAccParams p;
+    for (int g = 0; g < n_passes; ++g) {
+        if (pass_logits[g] == nullptr) return DAS_ERR_INVALID_ARG;
+        if (v4 ? !aligned16(pass_logits[g]) : (reinterpret_cast<uintptr_t>(pass_logits[g]) & 3u))
+            return DAS_ERR_MISALIGNED;
+        p.logits[g] = pass_logits[g];
+    }
+    for (int g = n_passes; g < DAS_MAX_PASS_GROUP; ++g) p.logits[g] = nullptr;
+    const McLayout L = mc_layout(*desc);
+    char* base = static_cast<char*>(state);
+    p.sum_p = reinterpret_cast<float*>(base + L.sum_p);
+    p.sum_ent = reinterpret_cast<float*>(base + L.sum_ent);
+    p.votes = reinterpret_cast<uint8_t*>(base + L.votes);
+    p.HW = (long long)desc->H * desc->W;
+    p.C = desc->C;
+    p.T_cap = desc->T_cap;
+    p.n_passes = n_passes;
+    p.pass_begin = pass_begin;
+    return dispatch_accumulate(p, desc->B, v4, desc->flags, (cudaStream_t)stream);
+}
+
+int das_mc_finalize(const das_mc_desc* desc, void* state, const float* labels, int T, float* vote_entropy,
+                    float* pred_entropy, float* bald, float* confidence, float* margin, uint8_t* weak_labels,
+                    float* image_scores, void* stream) {
+    int rc = mc_validate(desc);
+    if (rc != DAS_OK) return rc;
+    if (state == nullptr || T < 1 || T > desc->T_cap) return DAS_ERR_INVALID_ARG;
+    const bool probs = desc->flags & DAS_MC_PROBS, votes = desc->flags & DAS_MC_VOTES;
+    if (!votes && (vote_entropy || weak_labels)) return DAS_ERR_INVALID_ARG;
+    if (!probs && (pred_entropy || bald || confidence || margin)) return DAS_ERR_INVALID_ARG;
+    const bool v4 = use_vec4(*desc);
+    if (v4) {
+        const void* ptrs[] = {state, labels, vote_entropy, pred_entropy, bald, confidence, margin};
+        for (const void* q : ptrs)
+            if (q != nullptr && !aligned16(q)) return DAS_ERR_MISALIGNED;
+        if (weak_labels != nullptr && (reinterpret_cast<uintptr_t>(weak_labels) & 3u)) return DAS_ERR_MISALIGNED;
+    }
+    const McLayout L = mc_layout(*desc);
+    char* base = static_cast<char*>(state);
+    McFinParams p;
+    p.sum_p = reinterpret_cast<const float*>(base + L.sum_p);
+    p.sum_ent = reinterpret_cast<const float*>(base + L.sum_ent);
+    p.votes = reinterpret_cast<const uint8_t*>(base + L.votes);
+    p.labels = labels;
+    p.vote_entropy = vote_entropy;
+    p.pred_entropy = pred_entropy;
+    p.bald = bald;
+    p.confidence = confidence;
+    p.margin = margin;
+    p.weak_labels = weak_labels;
+    p.partials = reinterpret_cast<float*>(base + L.partials);
+    p.HW = (long long)desc->H * desc->W;
+    p.C = desc->C;
+    p.T_cap = desc->T_cap;
+    p.T = T;
+    p.blocks_per_image = L.blocks_per_image;
+    cudaStream_t st = (cudaStream_t)stream;
+    rc = dispatch_finalize(p, desc->B, v4, desc->flags, st);
+    if (rc != DAS_OK) return rc;
+    if (image_scores != nullptr) {
+        DAS_LAUNCH(mc_reduce_partials_kernel, desc->B, 32 * DAS_N_SCORES, 0, st, p.partials, L.blocks_per_image, p.HW,
+                   desc->flags, image_scores);
+        DAS_CHECK_LAUNCH();
+    }
+    return DAS_OK;
+}
+
+int das_mc_votes_ptr(const das_mc_desc* desc, void* state, uint8_t** votes) {
+    int rc = mc_validate(desc);
+    if (rc != DAS_OK) return rc;
+    if (state == nullptr || votes == nullptr || !(desc->flags & DAS_MC_VOTES)) return DAS_ERR_INVALID_ARG;
+    *votes = reinterpret_cast<uint8_t*>(static_cast<char*>(state) + mc_layout(*desc).votes);
+    return DAS_OK;
+}
+
+}  // extern "C"

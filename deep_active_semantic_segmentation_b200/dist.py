@@ -1,0 +1,127 @@
+"""Pool sharding over ranks (one process per GPU) and the tiny exchanges the path needs.
+
+The unlabeled pool shards by image: rank r scores the contiguous block
+[r*ceil(N/W), min(N, (r+1)*ceil(N/W))) with no communication.  The only exchanges are
+  * an all-gather of each rank's top-k (score, global index) candidates,
+  * an all-reduce of the pool min / max of the region score maps (mc_dropout.py:152-153),
+  * an all-gather of the per-image NMS pick sequences,
+  * for core-set, one tiny all-gather per greedy step (the arg-max key).
+Everything below works with any torch.distributed backend: NCCL with CUDA tensors on the GPU box,
+gloo with CPU tensors in the CPU tests.  Without an initialised process group it degrades to W = 1.
+"""
+from __future__ import annotations
+
+import heapq
+import math
+
+import torch
+import torch.distributed as td
+
+
+def world():
+    if td.is_available() and td.is_initialized():
+        return td.get_world_size(), td.get_rank()
+    return 1, 0
+
+
+def _comm_device():
+    """NCCL moves CUDA tensors, gloo moves CPU tensors."""
+    if td.get_backend() == "nccl":
+        return torch.device("cuda", torch.cuda.current_device())
+    return torch.device("cpu")
+
+
+def shard_bounds(n: int, world_size: int, rank: int):
+    per = -(-n // world_size) if n > 0 else 0
+    lo = min(n, rank * per)
+    return lo, min(n, lo + per)
+
+
+def gather_candidates(scores, ids, k: int):
+    """All-gather up to k (score, global id) candidates per rank -> python lists over all ranks.
+
+    scores/ids: 1-D tensors (any device) already restricted to the rank's best k, in rank-local order.
+    """
+    W, _ = world()
+    s = scores.detach().to(torch.float32).reshape(-1)
+    i = ids.detach().to(torch.int64).reshape(-1)
+    if W == 1:
+        return s.cpu().tolist(), i.cpu().tolist()
+    dev = _comm_device()
+    buf = torch.zeros(k, 2, dtype=torch.float64, device=dev)     # (score, id) - ids < 2^53 are exact
+    cnt = torch.tensor([s.numel()], dtype=torch.int64, device=dev)
+    if s.numel():
+        buf[: s.numel(), 0] = s.to(dev, torch.float64)
+        buf[: s.numel(), 1] = i.to(dev, torch.float64)
+    bufs = [torch.empty_like(buf) for _ in range(W)]
+    cnts = [torch.empty_like(cnt) for _ in range(W)]
+    td.all_gather(bufs, buf)
+    td.all_gather(cnts, cnt)
+    out_s, out_i = [], []
+    for b, c in zip(bufs, cnts):
+        n = int(c.item())
+        b = b[:n].cpu()
+        out_s += b[:, 0].tolist()      # float32 values widened exactly
+        out_i += [int(v) for v in b[:, 1].tolist()]
+    return out_s, out_i
+
+
+def merge_ranked(scores, ids, k: int, descending: bool):
+    """Stable global ranking of gathered candidates: score, then global index ascending - the order
+    Python's stable sorted() gives on the un-sharded pool (mc_dropout.py:195, ceal.py:69)."""
+    order = sorted(range(len(scores)), key=(lambda j: (-scores[j], ids[j])) if descending else (lambda j: (scores[j], ids[j])))
+    order = order[:k]
+    return [scores[j] for j in order], [ids[j] for j in order]
+
+
+def allreduce_minmax(minmax: torch.Tensor) -> torch.Tensor:
+    """Pool-global min / max from the per-rank (min, max) pair."""
+    W, _ = world()
+    if W == 1:
+        return minmax
+    dev = _comm_device()
+    t = torch.stack([-minmax[0], minmax[1]]).to(dev)
+    td.all_reduce(t, op=td.ReduceOp.MAX)
+    return torch.stack([-t[0], t[1]]).to(minmax.device)
+
+
+def gather_objects(obj):
+    """All-gather a small picklable object (per-image NMS sequences) -> list over ranks."""
+    W, _ = world()
+    if W == 1:
+        return [obj]
+    out = [None] * W
+    td.all_gather_object(out, obj)
+    return out
+
+
+def merge_nms_sequences(seqs, region_size: int, max_selection_count: float, H2: int, W2: int, stop: float = 0.01):
+    """Global greedy NMS == k-way merge of the image-local pick sequences.
+
+    seqs: list over images (global order) of [(score, r, c), ...] in pick order.
+    Order: score descending, ties by flat pool index (image, r, c) ascending = the first-flat-argmax
+    rule of mc_dropout.py:91.  Pick j+1 is taken iff j < ceil(K) and its score - the pool maximum
+    after pick j - is >= 0.01 (mc_dropout.py:87,105); the first pick is unconditional.
+    """
+    import numpy as np
+
+    stop32 = np.float32(stop)
+    heap = []
+    for i, seq in enumerate(seqs):
+        if seq:
+            s, r, c = seq[0]
+            heapq.heappush(heap, (-float(s), (i * H2 + r) * W2 + c, i, 0))
+    selected = [[] for _ in seqs]
+    count = 0
+    kmax = math.ceil(max_selection_count)
+    while heap and count < kmax:
+        negs, _, i, j = heapq.heappop(heap)
+        if count > 0 and np.float32(-negs) < stop32:
+            break
+        _, r, c = seqs[i][j]
+        selected[i].append((int(r), int(c), region_size, region_size))
+        count += 1
+        if j + 1 < len(seqs[i]):
+            s2, r2, c2 = seqs[i][j + 1]
+            heapq.heappush(heap, (-float(s2), (i * H2 + r2) * W2 + c2, i, j + 1))
+    return selected, count

@@ -1,0 +1,244 @@
+"""Tensor-level wrappers over the C ABI (include/das_b200.h).
+
+PyTorch is used for device memory and streams only: every function takes CUDA tensors, extracts
+`data_ptr()` / the current stream and calls libdas_b200.so through ctypes.  Nothing here computes
+scores on the host and nothing falls back to torch ops - a CPU tensor raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from typing import Iterable, Sequence
+
+import torch
+
+from . import _lib
+from ._lib import MC_PROBS, MC_VOTES, N_SCORES, SCORE_INDEX, DasError, McDesc, check
+
+MAP_NAMES = ("vote_entropy", "pred_entropy", "bald", "confidence", "margin")
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _need_cuda(t: torch.Tensor, name: str, dtype=None):
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise DasError(f"{name} must be a CUDA tensor (there is no CPU path)")
+    if dtype is not None and t.dtype != dtype:
+        raise DasError(f"{name} must be {dtype}, got {t.dtype}")
+    return t if t.is_contiguous() else t.contiguous()
+
+
+class MCState:
+    """Running Monte-Carlo state for one batch of B images (K1 accumulate + K2 finalize).
+
+    Mirrors the life of `outputs = torch.cuda.FloatTensor(B, MC_STEPS, H, W)` in the reference
+    (mc_dropout.py:37): created per batch, fed one stochastic forward at a time (or a group of them),
+    finalised into entropy maps and per-image scores.
+    """
+
+    def __init__(self, B: int, C_: int, H: int, W: int, T_cap: int, votes: bool = True, probs: bool = True,
+                 device=None):
+        self.lib = _lib.load()
+        self.desc = McDesc(B, C_, H, W, T_cap, (MC_VOTES if votes else 0) | (MC_PROBS if probs else 0))
+        self.B, self.C, self.H, self.W, self.T_cap = B, C_, H, W, T_cap
+        self.votes, self.probs = votes, probs
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        nbytes = C.c_size_t()
+        check(self.lib.das_mc_state_bytes(C.byref(self.desc), C.byref(nbytes)), "das_mc_state_bytes")
+        self.nbytes = nbytes.value
+        self.state = torch.empty(self.nbytes, dtype=torch.uint8, device=self.device)
+        self.n_passes = 0
+
+    def reset(self):
+        self.n_passes = 0
+
+    def accumulate(self, pass_logits: torch.Tensor | Sequence[torch.Tensor]):
+        """Consume one pass ([B,C,H,W] logits) or a group of passes (sequence of such tensors)."""
+        group = [pass_logits] if isinstance(pass_logits, torch.Tensor) else list(pass_logits)
+        start = 0
+        while start < len(group):
+            chunk = [_need_cuda(t, "logits", torch.float32) for t in group[start:start + _lib.MAX_PASS_GROUP]]
+            for t in chunk:
+                if tuple(t.shape) != (self.B, self.C, self.H, self.W):
+                    raise DasError(f"logits shape {tuple(t.shape)} != {(self.B, self.C, self.H, self.W)}")
+            arr = (C.c_void_p * len(chunk))(*[t.data_ptr() for t in chunk])
+            check(self.lib.das_mc_accumulate(C.byref(self.desc), _ptr(self.state), arr, len(chunk), self.n_passes,
+                                             _stream()), "das_mc_accumulate")
+            self.n_passes += len(chunk)
+            start += len(chunk)
+
+    def finalize(self, labels: torch.Tensor | None, maps: Iterable[str] = (), scores: bool = True,
+                 weak_labels: bool = False, scores_out: torch.Tensor | None = None) -> dict:
+        """-> {'scores': f32 [B,6] (column order _lib.SCORE_INDEX), <map name>: f32 [B,H,W], 'weak_labels': u8}.
+        scores_out: optional contiguous f32 [B,6] destination (e.g. a slice of a pool-wide score table)."""
+        if self.n_passes < 1:
+            raise DasError("finalize() before any accumulate()")
+        if labels is not None:
+            labels = _need_cuda(labels, "labels", torch.float32)
+            if tuple(labels.shape) != (self.B, self.H, self.W):
+                raise DasError(f"labels shape {tuple(labels.shape)} != {(self.B, self.H, self.W)}")
+        out = {}
+        bufs = {}
+        for name in maps:
+            if name not in MAP_NAMES:
+                raise DasError(f"unknown map {name!r}")
+            bufs[name] = torch.empty((self.B, self.H, self.W), dtype=torch.float32, device=self.device)
+        wl = torch.empty((self.B, self.H, self.W), dtype=torch.uint8, device=self.device) if weak_labels else None
+        if scores_out is not None:
+            if (not scores_out.is_cuda or scores_out.dtype != torch.float32 or not scores_out.is_contiguous()
+                    or tuple(scores_out.shape) != (self.B, N_SCORES)):
+                raise DasError("scores_out must be a contiguous CUDA float32 [B, 6] tensor")
+            sc = scores_out
+        else:
+            sc = torch.empty((self.B, N_SCORES), dtype=torch.float32, device=self.device) if scores else None
+        check(self.lib.das_mc_finalize(C.byref(self.desc), _ptr(self.state), _ptr(labels), self.n_passes,
+                                       *[_ptr(bufs.get(n)) for n in MAP_NAMES], _ptr(wl), _ptr(sc), _stream()),
+              "das_mc_finalize")
+        out.update(bufs)
+        if wl is not None:
+            out["weak_labels"] = wl
+        if sc is not None:
+            out["scores"] = sc
+        return out
+
+    def votes_tensor(self) -> torch.Tensor:
+        """u8 [B,T_cap,H,W] copy of the recorded votes (tests / debugging)."""
+        p = C.c_void_p()
+        check(self.lib.das_mc_votes_ptr(C.byref(self.desc), _ptr(self.state), C.byref(p)), "das_mc_votes_ptr")
+        off = p.value - self.state.data_ptr()
+        n = self.B * self.T_cap * self.H * self.W
+        return self.state[off:off + n].view(self.B, self.T_cap, self.H, self.W).clone()
+
+
+# ---------------------------------------------------------------------------------------------
+# region path
+# ---------------------------------------------------------------------------------------------
+
+def suppress_rects(maps: torch.Tensor, rects) -> None:
+    """In place: zero maps[i, r:r+h, c:c+w] for every (i, r, c, h, w) (mc_dropout.py:110-121)."""
+    maps_c = _need_cuda(maps, "maps", torch.float32)
+    if maps_c.data_ptr() != maps.data_ptr():
+        raise DasError("maps must be contiguous (modified in place)")
+    if len(rects) == 0:
+        return
+    r = torch.as_tensor(rects, dtype=torch.int32).reshape(-1, 5).to(maps.device)
+    B, H, W = maps.shape
+    check(_lib.load().das_suppress_rects(_ptr(maps), B, H, W, _ptr(r), r.shape[0], _stream()), "das_suppress_rects")
+
+
+def add_maps(a: torch.Tensor, b: torch.Tensor) -> None:
+    _need_cuda(a, "a", torch.float32)
+    b = _need_cuda(b, "b", torch.float32)
+    if not a.is_contiguous() or a.numel() != b.numel():
+        raise DasError("add_maps: a must be contiguous and the sizes must agree")
+    check(_lib.load().das_add_maps(_ptr(a), _ptr(b), a.numel(), _stream()), "das_add_maps")
+
+
+def new_minmax(device) -> torch.Tensor:
+    mm = torch.empty(2, dtype=torch.float32, device=device)
+    check(_lib.load().das_minmax_init(_ptr(mm), _stream()), "das_minmax_init")
+    return mm
+
+
+def box_sum(maps: torch.Tensor, R: int, minmax: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
+    """Stride-1 valid RxR box sums of maps [B,H,W] -> [B,H-R+1,W-R+1]; folds min/max into `minmax`."""
+    maps = _need_cuda(maps, "maps", torch.float32)
+    B, H, W = maps.shape
+    lib = _lib.load()
+    nbytes = C.c_size_t()
+    check(lib.das_box_sum_workspace_bytes(B, H, W, R, C.byref(nbytes)), "das_box_sum_workspace_bytes")
+    ws = torch.empty(nbytes.value, dtype=torch.uint8, device=maps.device)
+    if out is None:
+        out = torch.empty((B, H - R + 1, W - R + 1), dtype=torch.float32, device=maps.device)
+    elif not out.is_contiguous() or tuple(out.shape) != (B, H - R + 1, W - R + 1):
+        raise DasError("box_sum: bad `out`")
+    check(lib.das_box_sum(_ptr(maps), B, H, W, R, _ptr(out), _ptr(minmax), _ptr(ws), _stream()), "das_box_sum")
+    return out
+
+
+def minmax_normalise(score_maps: torch.Tensor, minmax: torch.Tensor) -> None:
+    if not score_maps.is_contiguous():
+        raise DasError("minmax_normalise: score_maps must be contiguous (modified in place)")
+    _need_cuda(score_maps, "score_maps", torch.float32)
+    check(_lib.load().das_minmax_normalise(_ptr(score_maps), score_maps.numel(), _ptr(minmax), _stream()),
+          "das_minmax_normalise")
+
+
+def nms_pick_bound(H2: int, W2: int, R: int) -> int:
+    """Picks of one image are pairwise >= R apart in the max-norm, so at most this many exist."""
+    return math.ceil(H2 / R) * math.ceil(W2 / R)
+
+
+def nms_sequences(score_maps: torch.Tensor, R: int, kmax: int, stop: float = 0.01):
+    """Per-image greedy NMS sequences; MUTATES score_maps. -> (scores [N,kmax], rc [N,kmax,2], count [N])."""
+    if not score_maps.is_contiguous():
+        raise DasError("nms_sequences: score_maps must be contiguous (modified in place)")
+    _need_cuda(score_maps, "score_maps", torch.float32)
+    N, H2, W2 = score_maps.shape
+    dev = score_maps.device
+    cs = torch.zeros((N, kmax), dtype=torch.float32, device=dev)
+    rc = torch.zeros((N, kmax, 2), dtype=torch.int32, device=dev)
+    cnt = torch.zeros((N,), dtype=torch.int32, device=dev)
+    check(_lib.load().das_nms_sequences(_ptr(score_maps), N, H2, W2, R, kmax, C.c_float(stop), _ptr(cs), _ptr(rc),
+                                        _ptr(cnt), _stream()), "das_nms_sequences")
+    return cs, rc, cnt
+
+
+# ---------------------------------------------------------------------------------------------
+# ranking
+# ---------------------------------------------------------------------------------------------
+
+def topk(scores: torch.Tensor, k: int, descending: bool, ids: torch.Tensor | None = None):
+    """First k of the stable sort of `scores` -> (scores [k], ids int64 [k]); ids default to positions."""
+    scores = _need_cuda(scores, "scores", torch.float32).reshape(-1)
+    n = scores.numel()
+    k = max(0, min(int(k), n))
+    out_s = torch.empty(k, dtype=torch.float32, device=scores.device)
+    out_i = torch.empty(k, dtype=torch.int64, device=scores.device)
+    if k == 0:
+        return out_s, out_i
+    if ids is not None:
+        ids = _need_cuda(ids, "ids", torch.int64).reshape(-1)
+        if ids.numel() != n:
+            raise DasError("topk: ids and scores differ in length")
+    check(_lib.load().das_topk(_ptr(scores), _ptr(ids), n, k, 1 if descending else 0, _ptr(out_s), _ptr(out_i), None,
+                               _stream()), "das_topk")
+    return out_s, out_i
+
+
+# ---------------------------------------------------------------------------------------------
+# core-set
+# ---------------------------------------------------------------------------------------------
+
+def kcenter_greedy(feats: torch.Tensor, centers: Sequence[int] | torch.Tensor, K: int):
+    """Single-GPU k-center greedy -> (picks int32 [K], min_dist f64 [N]) on the device."""
+    feats = _need_cuda(feats, "feats", torch.float32)
+    N, D = feats.shape
+    cen = torch.as_tensor(centers, dtype=torch.int32).reshape(-1).to(feats.device)
+    lib = _lib.load()
+    nbytes = C.c_size_t()
+    check(lib.das_kcenter_workspace_bytes(N, D, C.byref(nbytes)), "das_kcenter_workspace_bytes")
+    ws = torch.empty(nbytes.value, dtype=torch.uint8, device=feats.device)
+    picks = torch.empty(max(K, 1), dtype=torch.int32, device=feats.device)
+    min_d = torch.empty(N, dtype=torch.float64, device=feats.device)
+    check(lib.das_kcenter_greedy(_ptr(feats), N, D, _ptr(cen), cen.numel(), K, _ptr(picks), _ptr(min_d), _ptr(ws),
+                                 _stream()), "das_kcenter_greedy")
+    return picks[:K], min_d
+
+
+def kcenter_init(feats, row_begin, row_end, centers, min_d2, key2):
+    N, D = feats.shape
+    check(_lib.load().das_kcenter_init(_ptr(feats), N, D, row_begin, row_end, _ptr(centers), centers.numel(),
+                                       _ptr(min_d2), _ptr(key2), _stream()), "das_kcenter_init")
+
+
+def kcenter_step(feats, row_begin, row_end, centre_idx, min_d2, key2):
+    N, D = feats.shape
+    check(_lib.load().das_kcenter_step(_ptr(feats), N, D, row_begin, row_end, _ptr(centre_idx), _ptr(min_d2),
+                                       _ptr(key2), _stream()), "das_kcenter_step")

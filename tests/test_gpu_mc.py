@@ -1,0 +1,180 @@
+"""GPU parity of K1 (accumulate) + K2 (finalize) through the C ABI, against the numpy oracle."""
+import numpy as np
+import pytest
+import torch
+
+from deep_active_semantic_segmentation_b200 import synth
+from oracle import restate as R
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-5     # north_star: per-pixel and per-image scores within 1e-5 relative (float32)
+ATOL_MAP = 2e-6  # absolute floor for per-pixel maps: entropies of confident pixels are ~1e-4 and the
+                 # reference's own float32 formula carries ~1e-7 of rounding there
+ATOL_SCORE = 2e-7
+
+
+def _ops():
+    from deep_active_semantic_segmentation_b200 import ops
+    return ops
+
+
+def run_gpu(logits, labels, group, votes=True, probs=True, weak=False):
+    """logits numpy [B,T,C,H,W] -> dict of numpy outputs from the CUDA path."""
+    ops = _ops()
+    B, T, C, H, W = logits.shape
+    st = ops.MCState(B, C, H, W, T, votes=votes, probs=probs)
+    dev = [torch.from_numpy(np.ascontiguousarray(logits[:, t])).cuda() for t in range(T)]
+    for t0 in range(0, T, group):
+        st.accumulate(dev[t0:t0 + group])
+    maps = (["vote_entropy"] if votes else []) + ([m for m in ops.MAP_NAMES if m != "vote_entropy"] if probs else [])
+    lab = None if labels is None else torch.from_numpy(labels).cuda()
+    out = st.finalize(lab, maps=maps, scores=True, weak_labels=weak and votes)
+    res = {k: v.cpu().numpy() for k, v in out.items()}
+    if votes:
+        res["votes"] = st.votes_tensor().cpu().numpy()
+    torch.cuda.synchronize()
+    return res
+
+
+def check_against_oracle(res, logits, labels, votes=True, probs=True):
+    B, T, C, H, W = logits.shape
+    from deep_active_semantic_segmentation_b200._lib import SCORE_INDEX
+    for b in range(B):
+        o = R.mc_maps(logits[b], None if labels is None else labels[b], C)
+        osc = R.image_scores(o)
+        if votes:
+            np.testing.assert_array_equal(res["votes"][b, :T], o["votes"])            # index work: bit exact
+            np.testing.assert_allclose(res["vote_entropy"][b], o["vote_entropy"], rtol=RTOL, atol=ATOL_MAP)
+            np.testing.assert_allclose(res["scores"][b, SCORE_INDEX["vote_entropy"]], osc["vote_entropy"], rtol=RTOL, atol=ATOL_SCORE)
+        else:
+            assert np.isnan(res["scores"][b, SCORE_INDEX["vote_entropy"]])
+        if probs:
+            for name in ("pred_entropy", "confidence", "margin"):
+                np.testing.assert_allclose(res[name][b], o[name], rtol=RTOL, atol=ATOL_MAP, err_msg=name)
+            # BALD is a difference of two entropies: tolerance relative to the entropies' scale
+            np.testing.assert_allclose(res["bald"][b], o["bald"], rtol=RTOL, atol=ATOL_MAP + RTOL * float(o["pred_entropy"].max()))
+            for name in ("pred_entropy", "confidence", "margin", "expected_entropy"):
+                np.testing.assert_allclose(res["scores"][b, SCORE_INDEX[name]], osc[name], rtol=RTOL, atol=ATOL_SCORE, err_msg=name)
+            np.testing.assert_allclose(res["scores"][b, SCORE_INDEX["bald"]], osc["bald"], rtol=RTOL, atol=RTOL * float(osc["pred_entropy"]))
+        else:
+            assert np.isnan(res["scores"][b, SCORE_INDEX["bald"]])
+
+
+CASES = [
+    # (B, T, C, H, W, block)   odd H*W -> scalar path, H*W % 4 == 0 -> 128-bit path
+    (2, 5, 21, 65, 65, 8),
+    (3, 20, 19, 32, 64, 8),
+    (1, 1, 19, 16, 16, 4),      # CEAL: single pass
+    (2, 7, 2, 9, 7, 3),         # smallest class count, ragged
+    (1, 4, 32, 24, 20, 4),      # largest class count
+    (2, 33, 5, 12, 12, 4),      # more passes than one launch group can take
+]
+
+
+@pytest.mark.parametrize("B,T,C,H,W,block", CASES)
+@pytest.mark.parametrize("group", [1, 3, 64])
+def test_mc_matches_oracle(B, T, C, H, W, block, group):
+    gs = list(range(B))
+    logits = synth.pool_logits(7, gs, T, C, H, W, block)
+    labels = synth.pool_labels(7, gs, H, W, C, block)
+    res = run_gpu(logits, labels, min(group, T))
+    check_against_oracle(res, logits, labels)
+
+
+def test_mc_votes_only_and_probs_only_and_no_labels():
+    logits = synth.pool_logits(9, [0, 1], 6, 19, 20, 28, 4)
+    labels = synth.pool_labels(9, [0, 1], 20, 28, 19, 4)
+    check_against_oracle(run_gpu(logits, labels, 2, votes=True, probs=False), logits, labels, True, False)
+    check_against_oracle(run_gpu(logits, labels, 2, votes=False, probs=True), logits, labels, False, True)
+    check_against_oracle(run_gpu(logits, None, 6), logits, None)
+
+
+def test_mc_exact_ties_pick_first_class_and_labels_edge_values():
+    B, T, C, H, W = 1, 3, 7, 8, 8
+    logits = np.zeros((B, T, C, H, W), dtype=np.float32)       # every class ties -> vote 0
+    logits[0, 1, 3] = 2.0
+    logits[0, 1, 5] = 2.0                                       # tie between 3 and 5 -> 3
+    labels = np.zeros((B, H, W), dtype=np.float32)
+    labels[0, 0, :] = [-1, -0.0, 6, 6.5, 7, 255, np.nan, 3]     # valid iff not (l<0 or l>=C); NaN stays valid
+    res = run_gpu(logits, labels, 3, weak=True)
+    check_against_oracle(res, logits, labels)
+    assert (res["votes"][0, 0] == 0).all() and (res["votes"][0, 1] == 3).all()
+    wl = R.votes_from_logits(logits[0, 0]).copy()
+    wl[~R.valid_mask(labels[0], C)] = 255
+    np.testing.assert_array_equal(res["weak_labels"][0], wl)
+
+
+def test_mc_extreme_logits():
+    # large magnitudes / wide dynamic range: softmax must stay max-subtracted like ATen's
+    rng = np.random.default_rng(3)
+    logits = (rng.standard_normal((1, 4, 19, 8, 16)) * 30).astype(np.float32)
+    logits[0, 0, 2] += 500.0
+    logits[0, 1, 4] -= 500.0
+    res = run_gpu(logits, None, 4)
+    check_against_oracle(res, logits, None)
+    assert np.isfinite(res["scores"]).all()
+
+
+def test_full_size_properties():
+    """BASELINE config-2 shape (512x1024, C=19, T=20): size-independent properties instead of the oracle."""
+    ops = _ops()
+    from deep_active_semantic_segmentation_b200._lib import SCORE_INDEX as S
+    B, T, C, H, W = 2, 20, 19, 512, 1024
+    passes, lab = synth.device_pass_logits(1, 0, B, T, C, H, W, "cuda")
+
+    def run(order, group):
+        st = ops.MCState(B, C, H, W, T)
+        for t0 in range(0, T, group):
+            st.accumulate([passes[t] for t in order[t0:t0 + group]])
+        out = st.finalize(lab, maps=ops.MAP_NAMES, scores=True)
+        return out, st.votes_tensor()
+
+    out, votes = run(list(range(T)), 1)
+    # votes are exactly the per-pass argmax (integer work: bit exact, here against torch on the same device)
+    for t in (0, 7, 19):
+        assert torch.equal(votes[:, t].long(), passes[t].argmax(dim=1))
+    # grouping passes differently does not change anything (same per-pixel accumulation order)
+    out_g, votes_g = run(list(range(T)), 20)
+    assert torch.equal(votes, votes_g)
+    for k in list(ops.MAP_NAMES) + ["scores"]:
+        assert torch.equal(out[k], out_g[k]), k
+    # vote entropy is invariant under a permutation of the passes (histogram), bit for bit
+    perm = list(np.random.default_rng(0).permutation(T))
+    out_p, _ = run(perm, 4)
+    assert torch.equal(out["vote_entropy"], out_p["vote_entropy"])
+    torch.testing.assert_close(out["pred_entropy"], out_p["pred_entropy"], rtol=1e-5, atol=2e-6)
+    # ranges
+    ve, pe, bald, conf, marg = (out[k] for k in ops.MAP_NAMES)
+    assert ve.min() >= 0 and ve.max() <= np.log2(min(C, T)) + 1e-5
+    assert pe.min() >= 0 and pe.max() <= np.log2(C) + 1e-5
+    assert bald.min() >= -1e-5                       # mutual information is non-negative
+    assert conf.min() >= 1.0 / C - 1e-6 and conf.max() <= 1 + 1e-6 and marg.min() >= 0 and (marg <= conf + 1e-6).all()
+    invalid = (lab < 0) | (lab >= C)
+    assert (ve[invalid] == 0).all() and (pe[invalid] == 0).all() and (bald[invalid] == 0).all()
+    assert (conf[invalid] == 1).all() and (marg[invalid] == 1).all()
+    # image score == mean of the map over all pixels
+    for name in ops.MAP_NAMES:
+        ref = out[name].double().mean(dim=(1, 2)).float()
+        torch.testing.assert_close(out["scores"][:, S[name]], ref, rtol=1e-6, atol=1e-8)
+    torch.testing.assert_close(out["scores"][:, S["bald"]],
+                               out["scores"][:, S["pred_entropy"]] - out["scores"][:, S["expected_entropy"]], rtol=1e-5, atol=1e-6)
+
+
+def test_errors_are_loud():
+    ops = _ops()
+    from deep_active_semantic_segmentation_b200._lib import DasError
+    with pytest.raises(DasError):
+        ops.MCState(1, 33, 8, 8, 4)               # > DAS_MAX_CLASSES
+    with pytest.raises(DasError):
+        ops.MCState(1, 5, 8, 8, 256)              # > DAS_MAX_PASSES
+    st = ops.MCState(1, 5, 8, 8, 2)
+    with pytest.raises(DasError):
+        st.accumulate(torch.zeros(1, 5, 8, 8))     # CPU tensor: no CPU path
+    with pytest.raises(DasError):
+        st.accumulate(torch.zeros(1, 4, 8, 8, device="cuda"))   # wrong class count
+    with pytest.raises(DasError):
+        st.finalize(None)                          # nothing accumulated
+    st.accumulate([torch.zeros(1, 5, 8, 8, device="cuda")] * 2)
+    with pytest.raises(DasError):
+        st.accumulate(torch.zeros(1, 5, 8, 8, device="cuda"))   # state is full (T_cap = 2)

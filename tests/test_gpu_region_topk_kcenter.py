@@ -1,0 +1,202 @@
+"""GPU parity of the region kernels (suppress / box sum / min-max / NMS), K3 top-k and K4 k-center."""
+import numpy as np
+import pytest
+import torch
+
+from deep_active_semantic_segmentation_b200 import synth
+from oracle import restate as R
+from tests import golden_util as G
+
+pytestmark = pytest.mark.gpu
+
+
+def _ops():
+    from deep_active_semantic_segmentation_b200 import ops
+    return ops
+
+
+# ------------------------------------------------------------------ top-k
+
+def _check_topk(scores, k, descending):
+    ops = _ops()
+    s, i = ops.topk(torch.tensor(scores, dtype=torch.float32).cuda(), k, descending)
+    want = R.rank_topk([float(np.float32(v)) for v in scores], k, descending)
+    assert i.cpu().tolist() == want                                   # index work: bit exact
+    np.testing.assert_array_equal(s.cpu().numpy(), np.asarray(scores, dtype=np.float32)[want])
+
+
+@pytest.mark.parametrize("descending", [True, False])
+def test_topk_ties_negatives_and_edges(descending):
+    _check_topk([0.5, 0.25, 0.5, 0.75, 0.25, 0.5], 4, descending)
+    _check_topk([0.5, 0.25, 0.5, 0.75, 0.25, 0.5], 100, descending)       # k > n clamps
+    _check_topk([1.0], 1, descending)
+    _check_topk([-1.0, 0.0, -0.0, 3.0, -2.5, 0.0, -1.0], 7, descending)    # -0.0 == 0.0 is a tie
+    _check_topk([0.0] * 300, 17, descending)                               # all equal: pure index order
+    rng = np.random.default_rng(0)
+    _check_topk(np.round(rng.random(2975), 2).tolist(), 125, descending)   # pool size of config 2, many ties
+    _check_topk(rng.standard_normal(100_000).astype(np.float32).tolist(), 4096, descending)
+    ops = _ops()
+    s, i = ops.topk(torch.zeros(0, device="cuda"), 5, descending)
+    assert s.numel() == 0 and i.numel() == 0
+
+
+def test_topk_payload_ids_and_limits():
+    ops = _ops()
+    from deep_active_semantic_segmentation_b200._lib import DasError
+    sc = torch.tensor([3.0, 1.0, 2.0, 3.0], device="cuda")
+    ids = torch.tensor([40, 10, 20, 30], dtype=torch.int64, device="cuda")
+    s, i = ops.topk(sc, 3, True, ids)
+    assert i.cpu().tolist() == [40, 30, 20]        # stable on POSITION, payload carried along
+    with pytest.raises(DasError):
+        ops.topk(torch.zeros(10000, device="cuda"), 5000, True)     # > DAS_TOPK_MAX_K
+    with pytest.raises(DasError):
+        ops.topk(torch.zeros(4), 2, True)                           # CPU tensor
+
+
+# ------------------------------------------------------------------ region path
+
+def test_suppress_and_box_sum_match_oracle():
+    ops = _ops()
+    rng = np.random.default_rng(1)
+    for (B, H, W, Rg) in [(3, 65, 65, 17), (2, 40, 100, 8), (1, 33, 47, 33), (2, 16, 16, 1), (1, 130, 1100, 64)]:
+        maps = (rng.random((B, H, W)) * 4).astype(np.float32)
+        maps[rng.random(maps.shape) < 0.4] = 0
+        rects = [(0, 3, 5, 7, 9), (B - 1, H - 4, W - 6, 10, 10), (0, 0, 0, 2, W)]   # second one is clipped
+        d = torch.from_numpy(maps).cuda()
+        ops.suppress_rects(d, rects)
+        want_m = maps.copy()
+        for (i, r, c, h, w) in rects:
+            R.suppress_rects(want_m[i], [(r, c, h, w)])
+        np.testing.assert_array_equal(d.cpu().numpy(), want_m)
+        mm = ops.new_minmax("cuda")
+        out = ops.box_sum(d, Rg, mm).cpu().numpy()
+        want = np.stack([R.box_sum(want_m[b], Rg) for b in range(B)])
+        # fp64 sliding sums rounded once: equal to the exact oracle up to one float32 ulp
+        np.testing.assert_allclose(out, want, rtol=1.2e-7, atol=1e-9)
+        np.testing.assert_array_equal(mm.cpu().numpy(), np.array([out.min(), out.max()], dtype=np.float32))
+        # min/max accumulate over batches (mc_dropout.py:152-153 on the whole pool)
+        ops.box_sum(d * 2, Rg, mm)
+        np.testing.assert_array_equal(mm.cpu().numpy(), np.array([out.min(), 2 * out.max()], dtype=np.float32))
+        norm = torch.from_numpy(out).cuda()
+        mm2 = torch.tensor([out.min(), out.max()], device="cuda")
+        ops.minmax_normalise(norm, mm2)
+        np.testing.assert_array_equal(norm.cpu().numpy(), R.minmax_normalise(out))     # same float32 ops
+
+
+def _nms_gpu(maps, Rg, K):
+    from deep_active_semantic_segmentation_b200.active_selection import ActiveSelectionMCDropout
+    t = torch.from_numpy(maps.copy())
+    regions, count = ActiveSelectionMCDropout.square_nms(t, Rg, K)
+    return regions, count, t.numpy()
+
+
+def test_nms_matches_sequential_reference_loop():
+    rng = np.random.default_rng(5)
+    for trial in range(10):
+        N, H2, W2, Rg = int(rng.integers(1, 6)), int(rng.integers(6, 40)), int(rng.integers(6, 40)), int(rng.integers(2, 9))
+        m = rng.random((N, H2, W2)).astype(np.float32)
+        m[rng.random(m.shape) < 0.3] = 0
+        if trial % 3 == 0:
+            m = np.round(m, 1)               # many exact ties: first flat index must win
+        K = float(rng.integers(1, 40)) + 0.5
+        want = m.copy()
+        ref_regions, ref_count = R.square_nms(want, Rg, K)
+        regions, count, mutated = _nms_gpu(m, Rg, K)
+        assert (regions, count) == (ref_regions, ref_count)
+        np.testing.assert_array_equal(mutated, want)          # the caller's tensor is mutated like the reference's
+    # degenerate: everything below the stop threshold -> exactly one pick
+    regions, count, _ = _nms_gpu(np.full((3, 5, 5), 0.001, np.float32), 2, 4.0)
+    assert count == 1 and regions[0] == [(0, 0, 2, 2)]
+
+
+def test_nms_png_fixture_on_gpu():
+    """The reference's own data-free NMS case (active_selection/tests.py:213-231) through the CUDA path."""
+    ops = _ops()
+    g = G.load("nms_png")
+    Rg, K = int(g["R"]), int(g["K"])
+    d = torch.from_numpy(g["images"].astype(np.float32) / 256).cuda()
+    mm = ops.new_minmax("cuda")
+    maps = ops.box_sum(d, Rg, mm)
+    np.testing.assert_array_equal(maps.cpu().numpy(), g["raw_maps"])       # k/256 sums are exact
+    assert float(mm[1]) == 8860.890625
+    ops.minmax_normalise(maps, mm)
+    np.testing.assert_array_equal(maps.cpu().numpy(), g["norm_maps"])
+    regions, count, _ = _nms_gpu(maps.cpu().numpy(), Rg, K)
+    assert count == 10 and regions == G.regions_from_rows(g["regions"], 2)
+
+
+def test_nms_full_size_properties():
+    """Cityscapes-shaped extension (512x1024, R=128): picks of an image are pairwise >= R apart (max-norm),
+    scores are non-increasing along each sequence, every pick is the map maximum at its time."""
+    ops = _ops()
+    rng = np.random.default_rng(2)
+    m = rng.random((4, 385, 897)).astype(np.float32)
+    d = torch.from_numpy(m).cuda()
+    kmax = ops.nms_pick_bound(385, 897, 128)
+    cs, rc, cnt = ops.nms_sequences(d, 128, kmax, 0.01)
+    cs, rc, cnt = cs.cpu().numpy(), rc.cpu().numpy(), cnt.cpu().numpy()
+    for i in range(4):
+        n = cnt[i]
+        assert 1 <= n <= kmax
+        assert cs[i, 0] == m[i].max() and (np.diff(cs[i, :n]) <= 0).all()
+        pts = rc[i, :n]
+        dist = np.abs(pts[:, None, :] - pts[None, :, :]).max(-1) + np.eye(n, dtype=np.int64) * 10**6
+        assert dist.min() >= 128
+        seq = R.nms_sequence_single(m[i].copy(), 128, kmax)
+        assert [(r, c) for _, r, c in seq] == [tuple(p) for p in pts.tolist()]
+
+
+# ------------------------------------------------------------------ k-center
+
+def test_kcenter_toy_fixture_gpu():
+    from deep_active_semantic_segmentation_b200.active_selection import ActiveSelectionCoreSet
+    g = G.load("kcenter_toy")
+    sel = ActiveSelectionCoreSet(None, None, None)
+    assert sel._select_batch(g["features"], [6], 5) == [0, 2, 8, 4, 7]
+    assert abs(float(sel.last_min_distances.max()) - 1.41421) < 1e-5
+
+
+@pytest.mark.parametrize("name", ["coreset_small", "coreset_mid"])
+def test_kcenter_matches_reference_golden(name):
+    from deep_active_semantic_segmentation_b200.active_selection import ActiveSelectionCoreSet
+    g = G.load(name)
+    seed, N, D, L, K = (int(v) for v in g["meta"])
+    feats = synth.coreset_features(seed, N, D)
+    assert G.sha(feats) == str(g["features_sha"])
+    sel = ActiveSelectionCoreSet(None, None, None)
+    picks = sel._select_batch(feats.astype(np.float64), list(range(L)), K)
+    assert picks == g["picks"].tolist()                                   # index work: bit exact
+    # golden distances carry sklearn's cancellation noise where the true distance is 0 (see oracle test)
+    np.testing.assert_allclose(sel.last_min_distances.cpu().numpy(), g["min_dist"], rtol=1e-9, atol=1e-4)
+
+
+def test_kcenter_asserts_like_reference_and_rejects_lossy_features():
+    from deep_active_semantic_segmentation_b200.active_selection import ActiveSelectionCoreSet
+    from deep_active_semantic_segmentation_b200._lib import DasError
+    sel = ActiveSelectionCoreSet(None, None, None)
+    with pytest.raises(AssertionError):
+        sel._select_batch(np.zeros((4, 3)), [0], 1)          # all distances 0 -> argmax 0, already selected
+    with pytest.raises(DasError):
+        sel._select_batch(np.full((4, 3), 0.1), [0], 1)      # 0.1 is not a float32 value
+
+
+def test_kcenter_odd_dimension_and_baseline_size_properties():
+    ops = _ops()
+    rng = np.random.default_rng(3)
+    f = rng.standard_normal((257, 37)).astype(np.float32)    # D % 4 != 0 -> scalar path
+    picks, md = ops.kcenter_greedy(torch.from_numpy(f).cuda(), [5, 9], 20)
+    want, wm = R.kcenter_greedy(f, [5, 9], 20)
+    assert picks.cpu().tolist() == want
+    np.testing.assert_allclose(md.cpu().numpy(), wm, rtol=1e-9, atol=1e-6)
+    # BASELINE config 5 size: N=10000, D=2048, L=50, K=500
+    N, D, L, K = 10000, 2048, 50, 500
+    feats = torch.from_numpy(synth.coreset_features(11, N, D)).cuda()
+    picks, md = ops.kcenter_greedy(feats, list(range(L)), K)
+    p = picks.cpu().tolist()
+    assert len(set(p)) == K and not (set(p) & set(range(L)))
+    md = md.cpu().numpy()
+    assert (md[p] == 0).all() and (md[:L] == 0).all()
+    # greedy property: the radius after the last pick is <= the distance at which the last pick was taken
+    sub = feats[p + list(range(L))].double()
+    d_all = torch.cdist(feats.double(), sub).min(dim=1).values.cpu().numpy()
+    np.testing.assert_allclose(md, d_all, rtol=1e-9, atol=1e-5)

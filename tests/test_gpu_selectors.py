@@ -1,0 +1,167 @@
+"""GPU: the selector mirror (same method signatures as the reference's active_selection classes) must
+reproduce what the reference's own classes returned on the same synthetic pools (tests/golden/*.npz)."""
+import numpy as np
+import pytest
+import torch
+
+from tests import fakes
+from tests import golden_util as G
+
+pytestmark = pytest.mark.gpu
+
+RTOL, ATOL = 1e-5, 2e-7
+
+
+@pytest.fixture(autouse=True)
+def _synthetic_data_layer():
+    from deep_active_semantic_segmentation_b200.active_selection import base
+    from deep_active_semantic_segmentation_b200 import constants
+    old, old_T = base.paths_dataset.PathsDataset, constants.MC_STEPS
+    base.paths_dataset.PathsDataset = fakes.SyntheticPathsDataset
+    yield
+    base.paths_dataset.PathsDataset, constants.MC_STEPS = old, old_T
+
+
+def _set_T(T):
+    import sys
+    from deep_active_semantic_segmentation_b200 import constants
+    constants.MC_STEPS = T
+    if "constants" in sys.modules and hasattr(sys.modules["constants"], "MC_STEPS"):
+        sys.modules["constants"].MC_STEPS = T      # honoured like the reference's global (constants.py:6)
+
+
+def _factory(method, C, pool, crop, bs):
+    from deep_active_semantic_segmentation_b200.active_selection import get_active_selection_class
+    return get_active_selection_class(method, C, pool, crop, bs)
+
+
+def _paths(N):
+    return [str(i) for i in range(N)]
+
+
+def _idx(paths):
+    return [int(p) for p in paths]
+
+
+@pytest.mark.parametrize("name", ["mc_small", "mc_aligned", "mc_config1"])
+@pytest.mark.parametrize("pass_group", [1, 4])
+def test_mc_dropout_and_ceal_selectors_match_reference(name, pass_group):
+    g = G.load(name)
+    seed, N, T, C, H, W, block, k, bs = (int(v) for v in g["meta"])
+    logits, labels = G.pool_from_meta(seed, N, T, C, H, W, block, g["logits_sha"])
+    pool = fakes.Pool(logits, labels)
+    crop = H if H == W else -1
+    _set_T(T)
+
+    sel = _factory("variance", C, pool, crop, bs)
+    sel.pass_group = pass_group
+    model = fakes.ReplayModel(pool)
+    chosen = sel.get_vote_entropy_for_images(model, _paths(N), k)
+    assert isinstance(chosen, tuple) and _idx(chosen) == g["ve_selected"].tolist()
+    np.testing.assert_allclose(sel.last_scores, g["ve_scores"], rtol=RTOL, atol=ATOL)
+    assert not model.drop.training and model.dropout_train_calls == sum(model.calls.values()) == T * -(-N // bs)
+
+    # per-pixel maps of the first batch through the reference's private method signature
+    nb = min(bs, N)
+    ds = fakes.SyntheticPathsDataset(pool, _paths(nb), crop, include_labels=True)
+    ib = torch.stack([ds[i]["image"] for i in range(nb)]).cuda()
+    lb = torch.stack([ds[i]["label"] for i in range(nb)]).cuda()
+    maps = sel._get_vote_entropy_for_batch(fakes.ReplayModel(pool), ib, lb)
+    assert len(maps) == nb and maps[0].shape == (H, W)
+    np.testing.assert_allclose(torch.stack(maps).cpu().numpy(), g["ve_maps"], rtol=RTOL, atol=2e-6)
+
+    ceal = _factory("ceal_entropy", C, pool, crop, bs)
+    ent_sel, ent = ceal.get_maximum_entropy_samples(fakes.ReplayModel(pool), _paths(N), k)
+    assert _idx(ent_sel) == g["ceal_entropy_selected"].tolist()
+    np.testing.assert_allclose(ent, g["ceal_entropy"], rtol=RTOL, atol=ATOL)
+    conf_sel = ceal.get_least_confident_samples(fakes.ReplayModel(pool), _paths(N), k)
+    assert _idx(conf_sel) == g["ceal_conf_selected"].tolist()
+    np.testing.assert_allclose(ceal.last_scores, g["ceal_conf"], rtol=RTOL, atol=ATOL)
+    marg_sel = ceal.get_least_margin_samples(fakes.ReplayModel(pool), _paths(N), k)
+    assert _idx(marg_sel) == g["ceal_margin_selected"].tolist()
+    np.testing.assert_allclose(ceal.last_scores, g["ceal_margin"], rtol=RTOL, atol=ATOL)
+    fused = ceal.get_fusion_of_confidence_margin_entropy_samples(fakes.ReplayModel(pool), _paths(N), k)
+    assert len(fused) == min(k, N) and set(fused) <= set(ent_sel) | set(conf_sel) | set(marg_sel)
+    weak = ceal.get_weakly_labeled_data(fakes.ReplayModel(pool), _paths(N), float(g["weak_threshold"]), entropies=list(g["ceal_entropy"]))
+    assert _idx(weak.keys()) == g["weak_idx"].tolist()
+    for j, p in enumerate(weak):
+        assert weak[p].dtype == np.uint8
+        np.testing.assert_array_equal(weak[p], g["weak_labels"][j])
+
+
+@pytest.mark.parametrize("name", ["region_small", "region_mid"])
+def test_region_selector_matches_reference(name):
+    g = G.load(name)
+    seed, N, T, C, S, block, Rg, sel_size, bs = (int(v) for v in g["meta"])
+    logits, labels = G.pool_from_meta(seed, N, T, C, S, S, block, g["logits_sha"])
+    pool = fakes.Pool(logits, labels)
+    _set_T(T)
+    sel = _factory("variance", C, pool, S, bs)
+    model = fakes.ReplayModel(pool)
+    regions, count = sel.create_region_maps(model, _paths(N), G.regions_from_rows(g["existing"], N), Rg, sel_size)
+    assert count == int(g["count"])
+    want = {str(i): lst for i, lst in enumerate(G.regions_from_rows(g["regions"], N)) if lst}
+    assert regions == want                      # dict path -> [(r,c,R,R)], pick order preserved
+    assert not model.drop.training
+
+
+def test_mc_noise_selectors_match_reference():
+    g = G.load("noise_small")
+    seed, N, T, C, S, block, Rg, k, bs = (int(v) for v in g["meta"])
+    logits, labels = G.pool_from_meta(seed, N, 2 * T, C, S, S, block, g["logits_sha"])
+    pool = fakes.Pool(logits, labels)
+    _set_T(T)
+    sel = _factory("noise_variance", C, pool, S, bs)
+    m = fakes.ReplayModel(pool)
+    assert _idx(sel.get_vote_entropy_for_images_with_input_noise(m, _paths(N), k)) == g["input_noise_selected"].tolist()
+    np.testing.assert_allclose(sel.last_scores, g["input_noise_scores"], rtol=RTOL, atol=ATOL)
+    m = fakes.ReplayModel(pool)
+    assert _idx(sel.get_vote_entropy_for_images_with_feature_noise(m, _paths(N), k)) == g["feature_noise_selected"].tolist()
+    np.testing.assert_allclose(sel.last_scores, g["feature_noise_scores"], rtol=RTOL, atol=ATOL)
+    assert m.noisy_calls == sum(m.calls.values()) and not m.noisy_features      # flag set for every pass, then cleared
+    m = fakes.ReplayModel(pool)
+    assert _idx(sel.get_vote_entropy_for_batch_with_noise_and_vote_entropy(m, _paths(N), k)) == g["combined_selected"].tolist()
+    np.testing.assert_allclose(sel.last_scores, g["combined_scores"], rtol=RTOL, atol=ATOL)
+    assert m.noisy_calls == m.dropout_train_calls == sum(m.calls.values()) // 2
+    regions, count = sel.create_region_maps(fakes.ReplayModel(pool), _paths(N), G.regions_from_rows(g["existing"], N), Rg, 1)
+    assert count == int(g["count"])
+    assert regions == {str(i): lst for i, lst in enumerate(G.regions_from_rows(g["regions"], N)) if lst}
+
+
+def test_coreset_selector_matches_reference():
+    g = G.load("coreset_e2e")
+    seed, N, L, K, bs = (int(v) for v in g["meta"])
+    rng = np.random.Generator(np.random.Philox(key=[seed, 77]))
+    feats = rng.standard_normal(size=(N, 128, 64, 64), dtype=np.float32)
+    feats += (rng.integers(0, 4, size=(N, 1, 1, 1)) * 0.5).astype(np.float32)
+    assert G.sha(feats) == str(g["features_sha"])
+    pool = fakes.Pool(np.zeros((N, 1, 2, 64, 64), np.float32), None, feats)
+    sel = _factory("coreset", 2, pool, 64, bs)
+    model = fakes.ReplayModel(pool, "enet")
+    chosen = sel.get_k_center_greedy_selections(K, model, _paths(N)[L:], _paths(N)[:L])
+    assert _idx(chosen) == g["chosen"].tolist()
+    assert model.return_features is False
+
+
+def test_composed_mc_scores_and_factory_errors():
+    from deep_active_semantic_segmentation_b200 import synth
+    from oracle import restate as R
+    N, T, C, H, W = 5, 6, 19, 24, 40
+    logits = synth.pool_logits(3, list(range(N)), T, C, H, W, 8)
+    labels = synth.pool_labels(3, list(range(N)), H, W, C, 8)
+    pool = fakes.Pool(logits, labels)
+    _set_T(T)
+    sel = _factory("variance", C, pool, -1, 2)
+    chosen, allv = sel.get_mc_scores_for_images(fakes.ReplayModel(pool), _paths(N), 3, score="bald")
+    want = {k: [] for k in R.SCORE_NAMES}
+    for i in range(N):
+        s = R.image_scores(R.mc_maps(logits[i], labels[i], C))
+        for k in want:
+            want[k].append(float(s[k]))
+    for k in want:
+        np.testing.assert_allclose(allv[k], want[k], rtol=RTOL, atol=1e-6, err_msg=k)
+    assert _idx(chosen) == R.rank_topk(want["bald"], 3, True)
+    with pytest.raises(NotImplementedError):
+        _factory("no_such_method", C, pool, -1, 2)
+    with pytest.raises(IndexError):
+        sel.get_vote_entropy_for_images(fakes.ReplayModel(pool), [], 3)       # the reference fails the same way

@@ -180,3 +180,20 @@ def test_coreset_e2e_fixture():
     assert rows.shape == (N, 1152)
     picks, _ = R.kcenter_greedy(rows, list(range(L)), K)
     assert picks == g["chosen"].tolist()      # combined = already + candidates -> index == path
+
+
+def test_cpu_port_matches_restatement():
+    """oracle/cpu_port.py (the timed CPU baseline of bench.py) computes the same scores."""
+    import torch
+    from deep_active_semantic_segmentation_b200 import synth
+    from oracle import cpu_port
+
+    B, T, C, H, W = 2, 6, 19, 24, 40
+    logits = synth.pool_logits(5, list(range(B)), T, C, H, W, 8)
+    labels = synth.pool_labels(5, list(range(B)), H, W, C, 8)
+    got = cpu_port.score_batch([torch.from_numpy(np.ascontiguousarray(logits[:, t])) for t in range(T)],
+                               torch.from_numpy(labels), C)
+    for b in range(B):
+        want = R.image_scores(R.mc_maps(logits[b], labels[b], C))
+        for k in got:
+            np.testing.assert_allclose(got[k][b].item(), want[k], rtol=RTOL, atol=1e-6, err_msg=k)
