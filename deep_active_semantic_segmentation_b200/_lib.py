@@ -13,6 +13,7 @@ LIB_PATH = os.path.join(PKG, "libdas_b200.so")
 
 MC_VOTES = 1
 MC_PROBS = 2
+MC_SINGLE_SHOT = 4
 N_SCORES = 6
 SCORE_INDEX = {"vote_entropy": 0, "pred_entropy": 1, "bald": 2, "confidence": 3, "margin": 4, "expected_entropy": 5}
 MAX_CLASSES = 32
@@ -40,6 +41,8 @@ _PROTOTYPES = {
     "das_mc_reset": (_i, [C.POINTER(McDesc), _vp, _vp]),
     "das_mc_accumulate": (_i, [C.POINTER(McDesc), _vp, C.POINTER(_vp), _i, _i, _vp]),
     "das_mc_finalize": (_i, [C.POINTER(McDesc), _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "das_mc_accumulate_finalize": (_i, [C.POINTER(McDesc), _vp, C.POINTER(_vp), _i, _i, _vp, _vp, _vp, _vp, _vp, _vp,
+                                         _vp, _vp, _vp]),
     "das_mc_votes_ptr": (_i, [C.POINTER(McDesc), _vp, C.POINTER(_vp)]),
     "das_suppress_rects": (_i, [_vp, _i, _i, _i, _vp, _i, _vp]),
     "das_add_maps": (_i, [_vp, _vp, _sz, _vp]),

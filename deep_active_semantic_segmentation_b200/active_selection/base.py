@@ -3,6 +3,7 @@ every selector repeats).  The scoring itself happens in libdas_b200.so through .
 from __future__ import annotations
 
 import math
+import os
 import sys
 import types
 
@@ -11,7 +12,7 @@ from torch.utils.data import DataLoader
 
 from .. import constants as _own_constants
 from .. import dist, ops
-from .._lib import SCORE_INDEX, DasError
+from .._lib import MAX_PASS_GROUP, SCORE_INDEX, DasError
 
 # The reference selectors reach the data layer through the module attribute
 # `paths_dataset.PathsDataset` (mc_dropout.py:131, ceal.py:21, core_set.py:42).  The data layer is out
@@ -53,8 +54,12 @@ class ActiveSelectionBase:
         self.crop_size = crop_size
         self.dataloader_batch_size = dataloader_batch_size
         self.env = dataset_lmdb_env
-        #: Monte-Carlo passes held back and consumed by ONE das_mc_accumulate launch (1 = pure streaming)
-        self.pass_group = 1
+        #: Monte-Carlo passes held back and consumed by ONE launch.  1 = pure streaming (the running
+        #: accumulators round-trip HBM every pass); None = as many as fit in `pass_group_bytes` of logits -
+        #: with all T passes in one group the fused kernel keeps the accumulators in registers and the
+        #: only HBM traffic is the logits, once ("pass groups").
+        self.pass_group = None
+        self.pass_group_bytes = int(os.environ.get("DAS_PASS_GROUP_BYTES", 16 << 30))
         #: scores of the last pool pass, global image order (diagnostics / parity tests)
         self.last_scores = None
 
@@ -69,21 +74,32 @@ class ActiveSelectionBase:
         return DataLoader(ds, batch_size=self.dataloader_batch_size, shuffle=False, num_workers=0)
 
     # -- Monte-Carlo scoring of one batch --------------------------------------------------------
+    def _group_size(self, T, logits):
+        if self.pass_group is not None:
+            return max(1, min(int(self.pass_group), T))
+        per_pass = logits.numel() * logits.element_size()
+        return max(1, min(T, MAX_PASS_GROUP, self.pass_group_bytes // max(per_pass, 1)))
+
     def _mc_batch(self, forward, image_batch, label_batch, T, votes, probs, maps=(), weak_labels=False):
-        """T calls of `forward(image_batch)` -> K1 accumulate (streaming) -> K2 finalize."""
+        """T calls of `forward(image_batch)`; the logits are consumed in groups of G passes: all but the last
+        group by K1 (das_mc_accumulate), the last group by the fused K1+K2 kernel
+        (das_mc_accumulate_finalize).  G == T: nothing but the logits ever crosses HBM."""
         B, _, H, W = image_batch.shape
-        state = None
+        state, G = None, 1
         pending = []
         with torch.no_grad():
             for step in range(T):
                 logits = forward(image_batch)
                 if state is None:
-                    state = ops.MCState(B, logits.shape[1], H, W, T, votes=votes, probs=probs, device=logits.device)
+                    G = self._group_size(T, logits)
+                    state = ops.MCState(B, logits.shape[1], H, W, T, votes=votes, probs=probs, device=logits.device,
+                                        single_shot=(G >= T))
                 pending.append(logits)
-                if len(pending) >= self.pass_group or step == T - 1:
+                if step == T - 1:
+                    return state.score(pending, label_batch, maps=maps, scores=True, weak_labels=weak_labels)
+                if len(pending) >= G:
                     state.accumulate(pending)
                     pending = []
-        return state.finalize(label_batch, maps=maps, scores=True, weak_labels=weak_labels)
 
     # -- ranking -----------------------------------------------------------------------------------
     def _rank(self, local_scores, lo, images, k, descending):

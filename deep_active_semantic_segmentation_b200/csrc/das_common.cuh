@@ -44,7 +44,8 @@ constexpr int kNumSMs = 148;  // B200: 2 dies x 74 SMs
 // state layout shared by accumulate / finalize (offsets in bytes, all 256-byte aligned)
 struct McLayout {
     size_t sum_p, sum_ent, votes, partials, total;
-    int blocks_per_image;  // finalize blocks per image (partials rows)
+    int blocks_per_image;  // K2 blocks per image (256 threads)
+    int blocks_fused;      // fused K1+K2 blocks per image (128 threads); partials are sized for this
 };
 McLayout mc_layout(const das_mc_desc& d);
 int mc_validate(const das_mc_desc* d);

@@ -10,8 +10,9 @@ unsigned long long g_launch_count = 0;
 
 // class-count ranges compiled in separate translation units (see build.py)
 #define DAS_DECL_RANGE(LO, HI)                                                                         \
-    int dispatch_accumulate_##LO##_##HI(const McAccParams&, int, bool, int, cudaStream_t);             \
-    int dispatch_finalize_##LO##_##HI(const McFinParams&, int, bool, int, cudaStream_t);
+    int dispatch_accumulate_##LO##_##HI(const McAccParams&, int, int, int, cudaStream_t);             \
+    int dispatch_finalize_##LO##_##HI(const McFinParams&, int, int, int, cudaStream_t);               \
+    int dispatch_score_##LO##_##HI(const McScoreParams&, int, int, int, cudaStream_t);
 DAS_DECL_RANGE(2, 9)
 DAS_DECL_RANGE(10, 16)
 DAS_DECL_RANGE(17, 20)
@@ -19,7 +20,7 @@ DAS_DECL_RANGE(21, 24)
 DAS_DECL_RANGE(25, 28)
 DAS_DECL_RANGE(29, 32)
 
-int dispatch_accumulate(const McAccParams& p, int B, bool v4, int f, cudaStream_t st) {
+int dispatch_accumulate(const McAccParams& p, int B, int v4, int f, cudaStream_t st) {
     if (p.C <= 9) return dispatch_accumulate_2_9(p, B, v4, f, st);
     if (p.C <= 16) return dispatch_accumulate_10_16(p, B, v4, f, st);
     if (p.C <= 20) return dispatch_accumulate_17_20(p, B, v4, f, st);
@@ -27,7 +28,7 @@ int dispatch_accumulate(const McAccParams& p, int B, bool v4, int f, cudaStream_
     if (p.C <= 28) return dispatch_accumulate_25_28(p, B, v4, f, st);
     return dispatch_accumulate_29_32(p, B, v4, f, st);
 }
-int dispatch_finalize(const McFinParams& p, int B, bool v4, int f, cudaStream_t st) {
+int dispatch_finalize(const McFinParams& p, int B, int v4, int f, cudaStream_t st) {
     if (p.C <= 9) return dispatch_finalize_2_9(p, B, v4, f, st);
     if (p.C <= 16) return dispatch_finalize_10_16(p, B, v4, f, st);
     if (p.C <= 20) return dispatch_finalize_17_20(p, B, v4, f, st);
@@ -36,32 +37,59 @@ int dispatch_finalize(const McFinParams& p, int B, bool v4, int f, cudaStream_t 
     return dispatch_finalize_29_32(p, B, v4, f, st);
 }
 
+int dispatch_score(const McScoreParams& p, int B, int v4, int f, cudaStream_t st) {
+    const int C = p.acc.C;
+    if (C <= 9) return dispatch_score_2_9(p, B, v4, f, st);
+    if (C <= 16) return dispatch_score_10_16(p, B, v4, f, st);
+    if (C <= 20) return dispatch_score_17_20(p, B, v4, f, st);
+    if (C <= 24) return dispatch_score_21_24(p, B, v4, f, st);
+    if (C <= 28) return dispatch_score_25_28(p, B, v4, f, st);
+    return dispatch_score_29_32(p, B, v4, f, st);
+}
+
 int mc_validate(const das_mc_desc* d) {
     if (d == nullptr) return DAS_ERR_INVALID_ARG;
     if (d->B <= 0 || d->H <= 0 || d->W <= 0 || d->T_cap <= 0) return DAS_ERR_INVALID_ARG;
-    if ((d->flags & (DAS_MC_VOTES | DAS_MC_PROBS)) == 0 || (d->flags & ~(DAS_MC_VOTES | DAS_MC_PROBS)))
+    if ((d->flags & (DAS_MC_VOTES | DAS_MC_PROBS)) == 0 ||
+        (d->flags & ~(DAS_MC_VOTES | DAS_MC_PROBS | DAS_MC_SINGLE_SHOT)))
         return DAS_ERR_INVALID_ARG;
+    if ((d->flags & DAS_MC_SINGLE_SHOT) && d->T_cap > DAS_MAX_PASS_GROUP) return DAS_ERR_UNSUPPORTED;
     if (d->C < 2) return DAS_ERR_INVALID_ARG;
     if (d->C > DAS_MAX_CLASSES || d->T_cap > DAS_MAX_PASSES || d->B > 65535) return DAS_ERR_UNSUPPORTED;
     return DAS_OK;
 }
 
-static bool use_vec4(const das_mc_desc& d) { return ((long long)d.H * d.W) % 4 == 0; }
+// pixels per thread: K2 and the vote-only kernels use 128-bit accesses when H*W % 4 == 0; the kernels that
+// carry softmax accumulators use 64-bit accesses when H*W is even (see mc_inst.cu); otherwise scalar
+static int fin_vec(const das_mc_desc& d) { return ((long long)d.H * d.W) % 4 == 0 ? 4 : 1; }
+static int acc_vec(const das_mc_desc& d) {
+    const long long HW = (long long)d.H * d.W;
+    if (d.flags & DAS_MC_PROBS) return HW % 2 == 0 ? 2 : 1;
+    return HW % 4 == 0 ? 4 : 1;
+}
+// pointer alignment every float tensor of this batch must have (bytes): 16 / 8 / 4 by H*W % 4, % 2
+static uintptr_t float_align(const das_mc_desc& d) {
+    const long long HW = (long long)d.H * d.W;
+    return HW % 4 == 0 ? 16 : (HW % 2 == 0 ? 8 : 4);
+}
+static bool misaligned(const void* p, uintptr_t a) { return (reinterpret_cast<uintptr_t>(p) & (a - 1)) != 0; }
 
 McLayout mc_layout(const das_mc_desc& d) {
     McLayout L;
     const size_t HW = (size_t)d.H * d.W;
-    const int vec = use_vec4(d) ? 4 : 1;
+    const int vec = fin_vec(d), avec = acc_vec(d);
     L.blocks_per_image = (int)((HW + (size_t)kFinalizeThreads * vec - 1) / ((size_t)kFinalizeThreads * vec));
+    L.blocks_fused = (int)((HW + (size_t)kAccThreads * avec - 1) / ((size_t)kAccThreads * avec));
+    const bool keep = !(d.flags & DAS_MC_SINGLE_SHOT);
     size_t off = 0;
     L.sum_p = off;
-    if (d.flags & DAS_MC_PROBS) off += align_up((size_t)d.B * d.C * HW * sizeof(float), 256);
+    if (keep && (d.flags & DAS_MC_PROBS)) off += align_up((size_t)d.B * d.C * HW * sizeof(float), 256);
     L.sum_ent = off;
-    if (d.flags & DAS_MC_PROBS) off += align_up((size_t)d.B * HW * sizeof(float), 256);
+    if (keep && (d.flags & DAS_MC_PROBS)) off += align_up((size_t)d.B * HW * sizeof(float), 256);
     L.votes = off;
-    if (d.flags & DAS_MC_VOTES) off += align_up((size_t)d.B * d.T_cap * HW, 256);
+    if (keep && (d.flags & DAS_MC_VOTES)) off += align_up((size_t)d.B * d.T_cap * HW, 256);
     L.partials = off;
-    off += align_up((size_t)d.B * L.blocks_per_image * DAS_N_SCORES * sizeof(float), 256);
+    off += align_up((size_t)d.B * L.blocks_fused * DAS_N_SCORES * sizeof(float), 256);
     L.total = off;
     return L;
 }
@@ -85,6 +113,79 @@ __global__ void mc_reduce_partials_kernel(const float* partials, int blocks_per_
 }  // namespace das
 
 using namespace das;
+
+static int fill_acc_params(const das_mc_desc* desc, void* state, const float* const* pass_logits, int n_passes,
+                           int pass_begin, McAccParams* out) {
+    if (state == nullptr || pass_logits == nullptr) return DAS_ERR_INVALID_ARG;
+    if (n_passes < 1 || pass_begin < 0 || pass_begin + n_passes > desc->T_cap) return DAS_ERR_INVALID_ARG;
+    if (n_passes > DAS_MAX_PASS_GROUP) return DAS_ERR_UNSUPPORTED;
+    const uintptr_t al = float_align(*desc);
+    if (!aligned16(state)) return DAS_ERR_MISALIGNED;
+    McAccParams& p = *out;
+    for (int g = 0; g < n_passes; ++g) {
+        if (pass_logits[g] == nullptr) return DAS_ERR_INVALID_ARG;
+        if (misaligned(pass_logits[g], al)) return DAS_ERR_MISALIGNED;
+        p.logits[g] = pass_logits[g];
+    }
+    for (int g = n_passes; g < DAS_MAX_PASS_GROUP; ++g) p.logits[g] = nullptr;
+    const McLayout L = mc_layout(*desc);
+    char* base = static_cast<char*>(state);
+    p.sum_p = reinterpret_cast<float*>(base + L.sum_p);
+    p.sum_ent = reinterpret_cast<float*>(base + L.sum_ent);
+    p.votes = (desc->flags & DAS_MC_SINGLE_SHOT) || !(desc->flags & DAS_MC_VOTES)
+                  ? nullptr
+                  : reinterpret_cast<uint8_t*>(base + L.votes);
+    p.HW = (long long)desc->H * desc->W;
+    p.C = desc->C;
+    p.T_cap = desc->T_cap;
+    p.n_passes = n_passes;
+    p.pass_begin = pass_begin;
+    return DAS_OK;
+}
+
+static int fill_fin_params(const das_mc_desc* desc, void* state, const float* labels, int T, float* vote_entropy,
+                           float* pred_entropy, float* bald, float* confidence, float* margin, uint8_t* weak_labels,
+                           int blocks, McFinParams* out) {
+    if (state == nullptr || T < 1 || T > desc->T_cap) return DAS_ERR_INVALID_ARG;
+    const bool probs = desc->flags & DAS_MC_PROBS, votes = desc->flags & DAS_MC_VOTES;
+    if (!votes && (vote_entropy || weak_labels)) return DAS_ERR_INVALID_ARG;
+    if (!probs && (pred_entropy || bald || confidence || margin)) return DAS_ERR_INVALID_ARG;
+    {
+        const uintptr_t al = float_align(*desc);
+        const void* ptrs[] = {labels, vote_entropy, pred_entropy, bald, confidence, margin};
+        for (const void* q : ptrs)
+            if (q != nullptr && misaligned(q, al)) return DAS_ERR_MISALIGNED;
+        if (!aligned16(state) || (weak_labels != nullptr && misaligned(weak_labels, al / 4))) return DAS_ERR_MISALIGNED;
+    }
+    const McLayout L = mc_layout(*desc);
+    char* base = static_cast<char*>(state);
+    McFinParams& p = *out;
+    p.sum_p = reinterpret_cast<const float*>(base + L.sum_p);
+    p.sum_ent = reinterpret_cast<const float*>(base + L.sum_ent);
+    p.votes = reinterpret_cast<const uint8_t*>(base + L.votes);
+    p.labels = labels;
+    p.vote_entropy = vote_entropy;
+    p.pred_entropy = pred_entropy;
+    p.bald = bald;
+    p.confidence = confidence;
+    p.margin = margin;
+    p.weak_labels = weak_labels;
+    p.partials = reinterpret_cast<float*>(base + L.partials);
+    p.HW = (long long)desc->H * desc->W;
+    p.C = desc->C;
+    p.T_cap = desc->T_cap;
+    p.T = T;
+    p.blocks_per_image = blocks;
+    return DAS_OK;
+}
+
+static int reduce_partials(const das_mc_desc* desc, const McFinParams& p, float* image_scores, cudaStream_t st) {
+    if (image_scores == nullptr) return DAS_OK;
+    DAS_LAUNCH(mc_reduce_partials_kernel, desc->B, 32 * DAS_N_SCORES, 0, st, p.partials, p.blocks_per_image, p.HW,
+               desc->flags, image_scores);
+    DAS_CHECK_LAUNCH();
+    return DAS_OK;
+}
 
 extern "C" {
 
@@ -122,30 +223,12 @@ int das_mc_accumulate(const das_mc_desc* desc, void* state, const float* const* 
                       int pass_begin, void* stream) {
     int rc = mc_validate(desc);
     if (rc != DAS_OK) return rc;
-    if (state == nullptr || pass_logits == nullptr) return DAS_ERR_INVALID_ARG;
-    if (n_passes < 1 || pass_begin < 0 || pass_begin + n_passes > desc->T_cap) return DAS_ERR_INVALID_ARG;
-    if (n_passes > DAS_MAX_PASS_GROUP) return DAS_ERR_UNSUPPORTED;
-    const bool v4 = use_vec4(*desc);
-    if (!aligned16(state)) return DAS_ERR_MISALIGNED;
+    if (desc->flags & DAS_MC_SINGLE_SHOT) return DAS_ERR_INVALID_ARG;
     McAccParams p;
-    for (int g = 0; g < n_passes; ++g) {
-        if (pass_logits[g] == nullptr) return DAS_ERR_INVALID_ARG;
-        if (v4 ? !aligned16(pass_logits[g]) : (reinterpret_cast<uintptr_t>(pass_logits[g]) & 3u))
-            return DAS_ERR_MISALIGNED;
-        p.logits[g] = pass_logits[g];
-    }
-    for (int g = n_passes; g < DAS_MAX_PASS_GROUP; ++g) p.logits[g] = nullptr;
-    const McLayout L = mc_layout(*desc);
-    char* base = static_cast<char*>(state);
-    p.sum_p = reinterpret_cast<float*>(base + L.sum_p);
-    p.sum_ent = reinterpret_cast<float*>(base + L.sum_ent);
-    p.votes = reinterpret_cast<uint8_t*>(base + L.votes);
-    p.HW = (long long)desc->H * desc->W;
-    p.C = desc->C;
-    p.T_cap = desc->T_cap;
-    p.n_passes = n_passes;
-    p.pass_begin = pass_begin;
-    return dispatch_accumulate(p, desc->B, v4, desc->flags, (cudaStream_t)stream);
+    rc = fill_acc_params(desc, state, pass_logits, n_passes, pass_begin, &p);
+    if (rc != DAS_OK) return rc;
+    return dispatch_accumulate(p, desc->B, acc_vec(*desc), desc->flags & (DAS_MC_VOTES | DAS_MC_PROBS),
+                               (cudaStream_t)stream);
 }
 
 int das_mc_finalize(const das_mc_desc* desc, void* state, const float* labels, int T, float* vote_entropy,
@@ -153,51 +236,41 @@ int das_mc_finalize(const das_mc_desc* desc, void* state, const float* labels, i
                     float* image_scores, void* stream) {
     int rc = mc_validate(desc);
     if (rc != DAS_OK) return rc;
-    if (state == nullptr || T < 1 || T > desc->T_cap) return DAS_ERR_INVALID_ARG;
-    const bool probs = desc->flags & DAS_MC_PROBS, votes = desc->flags & DAS_MC_VOTES;
-    if (!votes && (vote_entropy || weak_labels)) return DAS_ERR_INVALID_ARG;
-    if (!probs && (pred_entropy || bald || confidence || margin)) return DAS_ERR_INVALID_ARG;
-    const bool v4 = use_vec4(*desc);
-    if (v4) {
-        const void* ptrs[] = {state, labels, vote_entropy, pred_entropy, bald, confidence, margin};
-        for (const void* q : ptrs)
-            if (q != nullptr && !aligned16(q)) return DAS_ERR_MISALIGNED;
-        if (weak_labels != nullptr && (reinterpret_cast<uintptr_t>(weak_labels) & 3u)) return DAS_ERR_MISALIGNED;
-    }
-    const McLayout L = mc_layout(*desc);
-    char* base = static_cast<char*>(state);
+    if (desc->flags & DAS_MC_SINGLE_SHOT) return DAS_ERR_INVALID_ARG;
     McFinParams p;
-    p.sum_p = reinterpret_cast<const float*>(base + L.sum_p);
-    p.sum_ent = reinterpret_cast<const float*>(base + L.sum_ent);
-    p.votes = reinterpret_cast<const uint8_t*>(base + L.votes);
-    p.labels = labels;
-    p.vote_entropy = vote_entropy;
-    p.pred_entropy = pred_entropy;
-    p.bald = bald;
-    p.confidence = confidence;
-    p.margin = margin;
-    p.weak_labels = weak_labels;
-    p.partials = reinterpret_cast<float*>(base + L.partials);
-    p.HW = (long long)desc->H * desc->W;
-    p.C = desc->C;
-    p.T_cap = desc->T_cap;
-    p.T = T;
-    p.blocks_per_image = L.blocks_per_image;
-    cudaStream_t st = (cudaStream_t)stream;
-    rc = dispatch_finalize(p, desc->B, v4, desc->flags, st);
+    rc = fill_fin_params(desc, state, labels, T, vote_entropy, pred_entropy, bald, confidence, margin, weak_labels,
+                         mc_layout(*desc).blocks_per_image, &p);
     if (rc != DAS_OK) return rc;
-    if (image_scores != nullptr) {
-        DAS_LAUNCH(mc_reduce_partials_kernel, desc->B, 32 * DAS_N_SCORES, 0, st, p.partials, L.blocks_per_image, p.HW,
-                   desc->flags, image_scores);
-        DAS_CHECK_LAUNCH();
-    }
-    return DAS_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    rc = dispatch_finalize(p, desc->B, fin_vec(*desc), desc->flags & (DAS_MC_VOTES | DAS_MC_PROBS), st);
+    if (rc != DAS_OK) return rc;
+    return reduce_partials(desc, p, image_scores, st);
+}
+
+int das_mc_accumulate_finalize(const das_mc_desc* desc, void* state, const float* const* pass_logits, int n_passes,
+                               int pass_begin, const float* labels, float* vote_entropy, float* pred_entropy,
+                               float* bald, float* confidence, float* margin, uint8_t* weak_labels,
+                               float* image_scores, void* stream) {
+    int rc = mc_validate(desc);
+    if (rc != DAS_OK) return rc;
+    if ((desc->flags & DAS_MC_SINGLE_SHOT) && pass_begin != 0) return DAS_ERR_INVALID_ARG;
+    McScoreParams q;
+    rc = fill_acc_params(desc, state, pass_logits, n_passes, pass_begin, &q.acc);
+    if (rc != DAS_OK) return rc;
+    rc = fill_fin_params(desc, state, labels, pass_begin + n_passes, vote_entropy, pred_entropy, bald, confidence,
+                         margin, weak_labels, mc_layout(*desc).blocks_fused, &q.fin);
+    if (rc != DAS_OK) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    rc = dispatch_score(q, desc->B, acc_vec(*desc), desc->flags & (DAS_MC_VOTES | DAS_MC_PROBS), st);
+    if (rc != DAS_OK) return rc;
+    return reduce_partials(desc, q.fin, image_scores, st);
 }
 
 int das_mc_votes_ptr(const das_mc_desc* desc, void* state, uint8_t** votes) {
     int rc = mc_validate(desc);
     if (rc != DAS_OK) return rc;
-    if (state == nullptr || votes == nullptr || !(desc->flags & DAS_MC_VOTES)) return DAS_ERR_INVALID_ARG;
+    if (state == nullptr || votes == nullptr || !(desc->flags & DAS_MC_VOTES) || (desc->flags & DAS_MC_SINGLE_SHOT))
+        return DAS_ERR_INVALID_ARG;
     *votes = reinterpret_cast<uint8_t*>(static_cast<char*>(state) + mc_layout(*desc).votes);
     return DAS_OK;
 }

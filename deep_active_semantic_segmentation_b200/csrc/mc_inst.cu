@@ -8,21 +8,49 @@
 
 namespace das {
 
+// Kernel configuration (measured with tools/k1_bench.cu on B200, profiles/r1_k1_variants.txt):
+//   PROBS kernels, even H*W : VEC = 2 (64-bit loads), accumulators in shared memory, 5-8 blocks/SM
+//                             (0.87-0.93 of the measured HBM peak; VEC = 4 needs 160-240 registers and
+//                             stays at 0.60-0.77 because only 8-12 warps fit)
+//   PROBS kernels, odd  H*W : VEC = 1 (class planes are mutually misaligned), accumulators in registers
+//   vote-only kernels       : VEC = 4 / 1, everything in registers (already at the copy roofline)
+// static + dynamic shared memory can exceed the 48 KB default limit -> always opt in.
+template <typename K>
+static int set_smem(K kernel, size_t bytes) {
+    if (bytes > 0) {
+        cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+        if (e != cudaSuccess) return cuda_fail(e);
+    }
+    return DAS_OK;
+}
+// blocks/SM asked from ptxas: registers/thread ~ VEC*C + 42, 512 threads*regs <= 64K
+constexpr int minb_vec2(int C) { return C <= 12 ? 8 : (C <= 21 ? 6 : (C <= 28 ? 5 : 4)); }
+constexpr int minb_vec1(int C) { return C <= 16 ? 8 : (C <= 24 ? 6 : 4); }
+
 template <int C>
-int launch_accumulate(const McAccParams& p, int B, bool vec4, int flags, cudaStream_t st) {
-    const int vec = vec4 ? 4 : 1;
+int launch_accumulate(const McAccParams& p, int B, int vec, int flags, cudaStream_t st) {
     const long long per_block = (long long)kAccThreads * vec;
     dim3 grid((unsigned)((p.HW + per_block - 1) / per_block), (unsigned)B);
     const bool probs = flags & DAS_MC_PROBS, votes = flags & DAS_MC_VOTES;
-#define DAS_ACC(V, P, Q) DAS_LAUNCH((mc_accumulate_kernel<C, V, P, Q>), grid, kAccThreads, 0, st, p)
-    if (vec4) {
-        if (probs && votes) DAS_ACC(4, true, true);
-        else if (probs) DAS_ACC(4, true, false);
-        else DAS_ACC(4, false, true);
+    const size_t smem2 = acc_smem_bytes(C, 2);
+#define DAS_ACC(V, P, Q, S, MB, BYTES)                                                              \
+    do {                                                                                            \
+        int rc__ = set_smem(mc_accumulate_kernel<C, V, P, Q, S, MB>, BYTES);                        \
+        if (rc__ != DAS_OK) return rc__;                                                            \
+        DAS_LAUNCH((mc_accumulate_kernel<C, V, P, Q, S, MB>), grid, kAccThreads, BYTES, st, p);     \
+    } while (0)
+    if (probs) {
+        if (vec == 2) {
+            if (votes) DAS_ACC(2, true, true, true, minb_vec2(C), smem2);
+            else DAS_ACC(2, true, false, true, minb_vec2(C), smem2);
+        } else if (vec == 1) {
+            if (votes) DAS_ACC(1, true, true, false, minb_vec1(C), 0);
+            else DAS_ACC(1, true, false, false, minb_vec1(C), 0);
+        } else return DAS_ERR_INVALID_ARG;
     } else {
-        if (probs && votes) DAS_ACC(1, true, true);
-        else if (probs) DAS_ACC(1, true, false);
-        else DAS_ACC(1, false, true);
+        if (vec == 4) DAS_ACC(4, false, true, false, 1, 0);
+        else if (vec == 1) DAS_ACC(1, false, true, false, 1, 0);
+        else return DAS_ERR_INVALID_ARG;
     }
 #undef DAS_ACC
     DAS_CHECK_LAUNCH();
@@ -30,7 +58,8 @@ int launch_accumulate(const McAccParams& p, int B, bool vec4, int flags, cudaStr
 }
 
 template <int C>
-int launch_finalize(const McFinParams& p, int B, bool vec4, int flags, cudaStream_t st) {
+int launch_finalize(const McFinParams& p, int B, int vec, int flags, cudaStream_t st) {
+    const bool vec4 = vec == 4;
     dim3 grid((unsigned)p.blocks_per_image, (unsigned)B);
     const bool probs = flags & DAS_MC_PROBS, votes = flags & DAS_MC_VOTES;
 #define DAS_FIN(V, P, Q) DAS_LAUNCH((mc_finalize_kernel<C, V, P, Q>), grid, kFinalizeThreads, 0, st, p)
@@ -49,29 +78,67 @@ int launch_finalize(const McFinParams& p, int B, bool vec4, int flags, cudaStrea
 }
 
 template <int C>
+int launch_score(const McScoreParams& p, int B, int vec, int flags, cudaStream_t st) {
+    dim3 grid((unsigned)p.fin.blocks_per_image, (unsigned)B);
+    const bool probs = flags & DAS_MC_PROBS, votes = flags & DAS_MC_VOTES;
+    const size_t smem2 = acc_smem_bytes(C, 2);
+#define DAS_SCORE(V, P, Q, S, MB, BYTES)                                                            \
+    do {                                                                                            \
+        int rc__ = set_smem(mc_score_kernel<C, V, P, Q, S, MB>, BYTES);                             \
+        if (rc__ != DAS_OK) return rc__;                                                            \
+        DAS_LAUNCH((mc_score_kernel<C, V, P, Q, S, MB>), grid, kAccThreads, BYTES, st, p);          \
+    } while (0)
+    if (probs) {
+        if (vec == 2) {
+            if (votes) DAS_SCORE(2, true, true, true, minb_vec2(C), smem2);
+            else DAS_SCORE(2, true, false, true, minb_vec2(C), smem2);
+        } else if (vec == 1) {
+            if (votes) DAS_SCORE(1, true, true, false, minb_vec1(C), 0);
+            else DAS_SCORE(1, true, false, false, minb_vec1(C), 0);
+        } else return DAS_ERR_INVALID_ARG;
+    } else {
+        if (vec == 4) DAS_SCORE(4, false, true, false, 1, 0);
+        else if (vec == 1) DAS_SCORE(1, false, true, false, 1, 0);
+        else return DAS_ERR_INVALID_ARG;
+    }
+#undef DAS_SCORE
+    DAS_CHECK_LAUNCH();
+    return DAS_OK;
+}
+
+template <int C>
 struct Range {
-    static int acc(const McAccParams& p, int B, bool v4, int f, cudaStream_t st) {
+    static int score(const McScoreParams& p, int B, int v4, int f, cudaStream_t st) {
+        if (p.acc.C == C) return launch_score<C>(p, B, v4, f, st);
+        return Range<C + 1>::score(p, B, v4, f, st);
+    }
+    static int acc(const McAccParams& p, int B, int v4, int f, cudaStream_t st) {
         if (p.C == C) return launch_accumulate<C>(p, B, v4, f, st);
         return Range<C + 1>::acc(p, B, v4, f, st);
     }
-    static int fin(const McFinParams& p, int B, bool v4, int f, cudaStream_t st) {
+    static int fin(const McFinParams& p, int B, int v4, int f, cudaStream_t st) {
         if (p.C == C) return launch_finalize<C>(p, B, v4, f, st);
         return Range<C + 1>::fin(p, B, v4, f, st);
     }
 };
 template <>
 struct Range<DAS_C_HI + 1> {
-    static int acc(const McAccParams&, int, bool, int, cudaStream_t) { return DAS_ERR_UNSUPPORTED; }
-    static int fin(const McFinParams&, int, bool, int, cudaStream_t) { return DAS_ERR_UNSUPPORTED; }
+    static int acc(const McAccParams&, int, int, int, cudaStream_t) { return DAS_ERR_UNSUPPORTED; }
+    static int fin(const McFinParams&, int, int, int, cudaStream_t) { return DAS_ERR_UNSUPPORTED; }
+    static int score(const McScoreParams&, int, int, int, cudaStream_t) { return DAS_ERR_UNSUPPORTED; }
 };
 
 #define DAS_CAT_(a, b, c) a##b##_##c
 #define DAS_CAT(a, b, c) DAS_CAT_(a, b, c)
-int DAS_CAT(dispatch_accumulate_, DAS_C_LO, DAS_C_HI)(const McAccParams& p, int B, bool v4, int f, cudaStream_t st) {
+int DAS_CAT(dispatch_accumulate_, DAS_C_LO, DAS_C_HI)(const McAccParams& p, int B, int v4, int f, cudaStream_t st) {
     return Range<DAS_C_LO>::acc(p, B, v4, f, st);
 }
-int DAS_CAT(dispatch_finalize_, DAS_C_LO, DAS_C_HI)(const McFinParams& p, int B, bool v4, int f, cudaStream_t st) {
+int DAS_CAT(dispatch_finalize_, DAS_C_LO, DAS_C_HI)(const McFinParams& p, int B, int v4, int f, cudaStream_t st) {
     return Range<DAS_C_LO>::fin(p, B, v4, f, st);
+}
+
+int DAS_CAT(dispatch_score_, DAS_C_LO, DAS_C_HI)(const McScoreParams& p, int B, int v4, int f, cudaStream_t st) {
+    return Range<DAS_C_LO>::score(p, B, v4, f, st);
 }
 
 }  // namespace das

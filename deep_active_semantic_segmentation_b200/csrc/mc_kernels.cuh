@@ -1,13 +1,13 @@
-// K1 (streaming softmax/argmax -> accumulate) and K2 (finalize + image pooling) kernel templates.
+// K1 (streaming softmax/argmax -> accumulate), K2 (finalize + image pooling) and the fused K1+K2 kernel.
 //
 // Data layout in HBM (all per batch of B images, HW = H*W pixels):
 //   logits   f32 [B,C,HW]      one buffer per Monte-Carlo pass, read exactly once (evict-first)
 //   sum_p    f32 [B,C,HW]      running sum_t softmax(x_t)            (same layout as the logits)
 //   sum_ent  f32 [B,HW]        running sum_t entropy(softmax(x_t))
 //   votes    u8  [B,T_cap,HW]  argmax of every pass (the reference's outputs[B,T,H,W], as bytes)
-// A thread owns VEC consecutive pixels (VEC = 4: one 128-bit load per class plane, needs HW % 4 == 0;
-// VEC = 1: 513x513-style planes whose class planes are mutually misaligned) and keeps
-// the whole class vector of those pixels in registers, so each logit is touched once.
+// A thread owns VEC consecutive pixels (VEC = 4 / 2: one 128 / 64-bit load per class plane, needs
+// HW % VEC == 0; VEC = 1: 513x513-style planes whose class planes are mutually misaligned)
+// and keeps the whole class vector of those pixels in registers, so each logit is touched once.
 #pragma once
 
 #include "das_common.cuh"
@@ -39,15 +39,29 @@ struct McFinParams {
     int C, T_cap, T, blocks_per_image;
 };
 
+// fused "last group": accumulate + finalize without writing the state back
+struct McScoreParams {
+    McAccParams acc;
+    McFinParams fin;
+};
+
+// ---- VEC-wide float / byte vectors ----------------------------------------------------------
 template <int VEC>
 struct VecT;
 template <>
 struct VecT<4> {
     using F = float4;
+    using U = uint32_t;
+};
+template <>
+struct VecT<2> {
+    using F = float2;
+    using U = uint16_t;
 };
 template <>
 struct VecT<1> {
     using F = float;
+    using U = uint8_t;
 };
 
 template <int VEC>
@@ -55,6 +69,10 @@ __device__ __forceinline__ void unpack(const typename VecT<VEC>::F& v, float* ou
 template <>
 __device__ __forceinline__ void unpack<4>(const float4& v, float* out) {
     out[0] = v.x, out[1] = v.y, out[2] = v.z, out[3] = v.w;
+}
+template <>
+__device__ __forceinline__ void unpack<2>(const float2& v, float* out) {
+    out[0] = v.x, out[1] = v.y;
 }
 template <>
 __device__ __forceinline__ void unpack<1>(const float& v, float* out) {
@@ -67,253 +85,290 @@ __device__ __forceinline__ float4 pack<4>(const float* in) {
     return make_float4(in[0], in[1], in[2], in[3]);
 }
 template <>
+__device__ __forceinline__ float2 pack<2>(const float* in) {
+    return make_float2(in[0], in[1]);
+}
+template <>
 __device__ __forceinline__ float pack<1>(const float* in) {
     return in[0];
 }
 
+template <int VEC>
+__device__ __forceinline__ typename VecT<VEC>::F ldg_stream_v(const float* p, uint64_t pol);
+template <>
+__device__ __forceinline__ float4 ldg_stream_v<4>(const float* p, uint64_t pol) {
+    return ldg_stream(reinterpret_cast<const float4*>(p), pol);
+}
+template <>
+__device__ __forceinline__ float2 ldg_stream_v<2>(const float* p, uint64_t pol) {
+    float2 v;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v2.f32 {%0,%1}, [%2], %3;"
+                 : "=f"(v.x), "=f"(v.y)
+                 : "l"(p), "l"(pol));
+    return v;
+}
+template <>
+__device__ __forceinline__ float ldg_stream_v<1>(const float* p, uint64_t pol) {
+    return ldg_stream(p, pol);
+}
+
+// VEC bytes (one per pixel) <-> memory
+template <int VEC>
+__device__ __forceinline__ uint32_t load_bytes(const uint8_t* p) {
+    return (uint32_t)*reinterpret_cast<const typename VecT<VEC>::U*>(p);
+}
+template <int VEC>
+__device__ __forceinline__ void store_bytes(uint8_t* p, uint32_t w) {
+    *reinterpret_cast<typename VecT<VEC>::U*>(p) = (typename VecT<VEC>::U)w;
+}
+
 constexpr int kAccThreads = 128;
 
-// ---------------------------------------------------------------------------------------------
-// K1: consume n_passes passes of logits for VEC pixels per thread.
+// Running accumulators of a thread: C x VEC float32.  Two homes:
+//   registers      (SMEM = false)  - no extra instructions, but C*VEC live registers next to the C*VEC
+//                                    registers that hold the in-flight logits (VEC=4, C=19: 224 regs, 8 warps/SM)
+//   shared memory  (SMEM = true)   - one conflict-free LDS/STS per class and pass ([c][thread] vectors); the
+//                                    register file only holds in-flight logits, more warps fit per SM and more
+//                                    bytes are in flight (the kernel is latency bound, not issue bound;
+//                                    profiles/r1_k1_notes.md)
+template <int C, int VEC, bool SMEM>
+struct Acc {
+    float r[SMEM ? 1 : C][VEC];
+    typename VecT<VEC>::F* s;  // SMEM: &smem[tid], stride kAccThreads between classes
+    __device__ __forceinline__ void get(int c, float* out) const {
+        if (SMEM)
+            unpack<VEC>(s[c * kAccThreads], out);
+        else {
+#pragma unroll
+            for (int j = 0; j < VEC; ++j) out[j] = r[SMEM ? 0 : c][j];
+        }
+    }
+    __device__ __forceinline__ void set(int c, const float* in) {
+        if (SMEM)
+            s[c * kAccThreads] = pack<VEC>(in);
+        else {
+#pragma unroll
+            for (int j = 0; j < VEC; ++j) r[SMEM ? 0 : c][j] = in[j];
+        }
+    }
+};
+
+constexpr size_t acc_smem_bytes(int C, int VEC) { return (size_t)C * kAccThreads * VEC * sizeof(float); }
+
+// One Monte-Carlo pass for the VEC pixels of a thread: loads the C logits of each pixel once (streaming, evict
+// first), returns the votes packed one byte per pixel and updates the running accumulators.
 //   vote   v   = first argmax_c x_c                                     (mc_dropout.py:40)
 //   softmax p_c = 2^(x_c*log2e - m*log2e) / s, s = sum_c 2^(...)        (nn.Softmax2d, ceal.py:111)
 //   entropy of the pass: -sum p_c log2 p_c = log2 s - (sum_c e_c y_c)/s, y_c = (x_c - m) log2e <= 0
 //     (log-sum-exp form of ceal.py:118: one log2 per pixel instead of one per logit; it differs from
 //      the reference's "+1e-12" form by < 2e-12 per class and has no cancellation, both terms >= 0)
-// ---------------------------------------------------------------------------------------------
-template <int C, int VEC, bool PROBS, bool VOTES>
-__global__ void __launch_bounds__(kAccThreads) mc_accumulate_kernel(const McAccParams p) {
-    using F = typename VecT<VEC>::F;
-    const long long pix = ((long long)blockIdx.x * kAccThreads + threadIdx.x) * VEC;
-    if (pix >= p.HW) return;
-    const int b = blockIdx.y;
-    const size_t img_off = (size_t)b * C * p.HW + pix;
-    const uint64_t pol_stream = policy_evict_first();
-    const uint64_t pol_keep = policy_evict_last();
-
-    float acc[PROBS ? C : 1][VEC];
-    float ent[VEC];
-    if (PROBS) {
-        if (p.pass_begin == 0) {
+template <int C, int VEC, bool PROBS, bool VOTES, bool SMEM>
+__device__ __forceinline__ uint32_t mc_pass(const float* __restrict__ xp, long long HW, uint64_t pol,
+                                            Acc<C, VEC, SMEM>& acc, float* ent) {
+    float x[C][VEC];
 #pragma unroll
-            for (int c = 0; c < C; ++c)
+    for (int c = 0; c < C; ++c) unpack<VEC>(ldg_stream_v<VEC>(xp + (size_t)c * HW, pol), x[c]);
+    uint32_t vote_word = 0;
+    float inv[VEC];
 #pragma unroll
-                for (int j = 0; j < VEC; ++j) acc[c][j] = 0.f;
+    for (int j = 0; j < VEC; ++j) {
+        float m = x[0][j];
 #pragma unroll
-            for (int j = 0; j < VEC; ++j) ent[j] = 0.f;
-        } else {
+        for (int c = 1; c < C; ++c) m = fmaxf(m, x[c][j]);
+        if (VOTES) {
+            int v = 0;
+#pragma unroll
+            for (int c = C - 1; c >= 0; --c) v = (x[c][j] == m) ? c : v;  // first max wins
+            vote_word |= (uint32_t)v << (8 * j);
+        }
+        if (PROBS) {
+            const float mL = m * kLog2e;
+            float s = 0.f, a = 0.f;
 #pragma unroll
             for (int c = 0; c < C; ++c) {
-                F v = ldg_hint(reinterpret_cast<const F*>(p.sum_p + img_off + (size_t)c * p.HW), pol_keep);
-                unpack<VEC>(v, acc[c]);
+                const float y = fmaf(x[c][j], kLog2e, -mL);
+                const float e = ex2_approx(y);
+                s += e;
+                a = fmaf(e, y, a);
+                x[c][j] = e;
             }
-            F e = ldg_hint(reinterpret_cast<const F*>(p.sum_ent + (size_t)b * p.HW + pix), pol_keep);
-            unpack<VEC>(e, ent);
+            inv[j] = __frcp_rn(s);
+            ent[j] += log2f(s) - a * inv[j];
         }
     }
-
-    for (int g = 0; g < p.n_passes; ++g) {
-        const float* xp = p.logits[g] + img_off;
-        float x[C][VEC];
-#pragma unroll
-        for (int c = 0; c < C; ++c) {
-            F v = ldg_stream(reinterpret_cast<const F*>(xp + (size_t)c * p.HW), pol_stream);
-            unpack<VEC>(v, x[c]);
-        }
-        uint32_t vote_word = 0;
-#pragma unroll
-        for (int j = 0; j < VEC; ++j) {
-            float m = x[0][j];
-#pragma unroll
-            for (int c = 1; c < C; ++c) m = fmaxf(m, x[c][j]);
-            if (VOTES) {
-                int v = 0;
-#pragma unroll
-                for (int c = C - 1; c >= 0; --c) v = (x[c][j] == m) ? c : v;  // first max wins
-                vote_word |= (uint32_t)v << (8 * j);
-            }
-            if (PROBS) {
-                const float mL = m * kLog2e;
-                float s = 0.f, a = 0.f;
-#pragma unroll
-                for (int c = 0; c < C; ++c) {
-                    const float y = fmaf(x[c][j], kLog2e, -mL);
-                    const float e = ex2_approx(y);
-                    s += e;
-                    a = fmaf(e, y, a);
-                    x[c][j] = e;
-                }
-                const float inv = __frcp_rn(s);
-#pragma unroll
-                for (int c = 0; c < C; ++c) acc[c][j] = fmaf(x[c][j], inv, acc[c][j]);
-                ent[j] += log2f(s) - a * inv;
-            }
-        }
-        if (VOTES) {
-            uint8_t* vp = p.votes + ((size_t)b * p.T_cap + (p.pass_begin + g)) * p.HW + pix;
-            if (VEC == 4)
-                *reinterpret_cast<uint32_t*>(vp) = vote_word;
-            else
-                *vp = (uint8_t)vote_word;
-        }
-    }
-
     if (PROBS) {
 #pragma unroll
-        for (int c = 0; c < C; ++c)
-            stg_hint(reinterpret_cast<F*>(p.sum_p + img_off + (size_t)c * p.HW), pack<VEC>(acc[c]), pol_keep);
-        stg_hint(reinterpret_cast<F*>(p.sum_ent + (size_t)b * p.HW + pix), pack<VEC>(ent), pol_keep);
+        for (int c = 0; c < C; ++c) {
+            float a[VEC];
+            acc.get(c, a);
+#pragma unroll
+            for (int j = 0; j < VEC; ++j) a[j] = fmaf(x[c][j], inv[j], a[j]);
+            acc.set(c, a);
+        }
+    }
+    return vote_word;
+}
+
+// initialise the accumulators: zeros for the first group, otherwise the state written by earlier groups
+template <int C, int VEC, bool SMEM>
+__device__ __forceinline__ void mc_acc_init(Acc<C, VEC, SMEM>& acc, float* ent, bool first, const float* sum_p,
+                                            const float* sum_ent, size_t img_off, size_t map_off, long long HW) {
+    using F = typename VecT<VEC>::F;
+    float z[VEC];
+    if (first) {
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) z[j] = 0.f, ent[j] = 0.f;
+#pragma unroll
+        for (int c = 0; c < C; ++c) acc.set(c, z);
+    } else {
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+            unpack<VEC>(*reinterpret_cast<const F*>(sum_p + img_off + (size_t)c * HW), z);
+            acc.set(c, z);
+        }
+        unpack<VEC>(*reinterpret_cast<const F*>(sum_ent + map_off), ent);
     }
 }
 
 // ---------------------------------------------------------------------------------------------
-// K2: state -> per-pixel maps + per-block partial sums of every score.
-//   vote entropy: per-thread byte histogram of the T votes in shared memory (bank = lane, so no
-//   conflicts), then VE = sum_c ascending -(p log2(p + 1e-12)), p = n_c / T, through a T+1 entry table
-//   evaluated with the reference's float32 formula (mc_dropout.py:46-48).
-//   predictive entropy / confidence / margin on p_bar = sum_p / T with the reference's formulas
-//   (ceal.py:36,84-90,116-118); BALD = pred_entropy - sum_ent / T.
+// K1: consume n_passes passes of logits, add to the running state in HBM (streaming form).
 // ---------------------------------------------------------------------------------------------
-template <int C, int VEC, bool PROBS, bool VOTES>
-__global__ void __launch_bounds__(kFinalizeThreads) mc_finalize_kernel(const McFinParams p) {
+template <int C, int VEC, bool PROBS, bool VOTES, bool SMEM, int MINB>
+__global__ void __launch_bounds__(kAccThreads, MINB) mc_accumulate_kernel(const McAccParams p) {
     using F = typename VecT<VEC>::F;
-    constexpr int NT = kFinalizeThreads;
-    __shared__ uint32_t hist32[VOTES ? C * NT * VEC / 4 : 1];
-    __shared__ float lut[VOTES ? 256 : 1];
-    __shared__ float red[DAS_N_SCORES][NT / 32];
-    uint8_t* hist8 = reinterpret_cast<uint8_t*>(hist32);
-
-    const int tid = threadIdx.x;
+    extern __shared__ float4 acc_smem[];
+    const long long pix = ((long long)blockIdx.x * kAccThreads + threadIdx.x) * VEC;
+    if (pix >= p.HW) return;
     const int b = blockIdx.y;
-    const long long pix = ((long long)blockIdx.x * NT + tid) * VEC;
-    const bool active = pix < p.HW;
-    const float Tf = (float)p.T;
+    const size_t img_off = (size_t)b * C * p.HW + pix;
+    const size_t map_off = (size_t)b * p.HW + pix;
+    const uint64_t pol_stream = policy_evict_first();
 
-    if (VOTES) {
-        for (int n = tid; n <= p.T; n += NT) {
-            const float pr = (float)n / Tf;
-            lut[n] = pr * log2f(pr + kEps);
-        }
+    Acc<C, VEC, SMEM> acc;
+    acc.s = reinterpret_cast<F*>(acc_smem) + threadIdx.x;
+    float ent[VEC];
+    if (PROBS) mc_acc_init<C, VEC, SMEM>(acc, ent, p.pass_begin == 0, p.sum_p, p.sum_ent, img_off, map_off, p.HW);
+
+    for (int g = 0; g < p.n_passes; ++g) {
+        const uint32_t vote_word = mc_pass<C, VEC, PROBS, VOTES, SMEM>(p.logits[g] + img_off, p.HW, pol_stream, acc, ent);
+        if (VOTES) store_bytes<VEC>(p.votes + ((size_t)b * p.T_cap + (p.pass_begin + g)) * p.HW + pix, vote_word);
+    }
+
+    if (PROBS) {
 #pragma unroll
         for (int c = 0; c < C; ++c) {
-            if (VEC == 4)
-                hist32[c * NT + tid] = 0u;
-            else
-                hist8[c * NT + tid] = 0;
+            float a[VEC];
+            acc.get(c, a);
+            *reinterpret_cast<F*>(p.sum_p + img_off + (size_t)c * p.HW) = pack<VEC>(a);
         }
-        __syncthreads();
+        *reinterpret_cast<F*>(p.sum_ent + map_off) = pack<VEC>(ent);
     }
+}
 
-    float sc[DAS_N_SCORES][VEC];
-#pragma unroll
-    for (int k = 0; k < DAS_N_SCORES; ++k)
-#pragma unroll
-        for (int j = 0; j < VEC; ++j) sc[k][j] = 0.f;
+// ---- pieces shared by K2 and the fused kernel ---------------------------------------------------
 
-    if (active) {
-        bool valid[VEC];
-        if (p.labels != nullptr) {
-            float lab[VEC];
-            unpack<VEC>(*reinterpret_cast<const F*>(p.labels + (size_t)b * p.HW + pix), lab);
+// per-thread byte histogram of votes in shared memory: hist8[(class * NT + tid) * VEC + pixel]
+// (a thread's counters of one class form one VEC-byte word; the bank is a function of tid only -> no conflicts)
+template <int C, int VEC, int NT>
+__device__ __forceinline__ void hist_setup(uint8_t* hist8, float* lut, int T, int tid) {
+    const float Tf = (float)T;
+    for (int n = tid; n <= T; n += NT) {
+        const float pr = (float)n / Tf;
+        lut[n] = pr * log2f(pr + kEps);  // p * log2(p + 1e-12), p = n / T in float32 (mc_dropout.py:47-48)
+    }
 #pragma unroll
-            for (int j = 0; j < VEC; ++j) valid[j] = !((lab[j] < 0.f) || (lab[j] >= (float)C));  // mc_dropout.py:45
-        } else {
+    for (int c = 0; c < C; ++c) store_bytes<VEC>(hist8 + (size_t)(c * NT + tid) * VEC, 0u);
+    __syncthreads();
+}
+template <int VEC, int NT>
+__device__ __forceinline__ void hist_add(uint8_t* hist8, uint32_t vote_word, int tid) {
 #pragma unroll
-            for (int j = 0; j < VEC; ++j) valid[j] = true;
-        }
+    for (int j = 0; j < VEC; ++j) hist8[(((vote_word >> (8 * j)) & 0xff) * NT + tid) * VEC + j] += 1;
+}
+// VE = sum over classes ascending of -(p log2(p + 1e-12)) (mc_dropout.py:46-48)
+template <int C, int VEC, int NT>
+__device__ __forceinline__ void hist_vote_entropy(const uint8_t* hist8, const float* lut, int tid, float* ve) {
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) ve[j] = 0.f;
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+        const uint32_t w = load_bytes<VEC>(hist8 + (size_t)(c * NT + tid) * VEC);
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) ve[j] = ve[j] - lut[(w >> (8 * j)) & 0xff];
+    }
+}
 
-        if (PROBS) {
-            float pe[VEC], top1[VEC], top2[VEC];
+template <int C, int VEC>
+__device__ __forceinline__ void load_valid(const float* labels, size_t map_off, bool* valid) {
+    if (labels != nullptr) {
+        float lab[VEC];
+        unpack<VEC>(*reinterpret_cast<const typename VecT<VEC>::F*>(labels + map_off), lab);
 #pragma unroll
-            for (int j = 0; j < VEC; ++j) pe[j] = 0.f, top1[j] = -1.f, top2[j] = -1.f;
-            const float* sp = p.sum_p + (size_t)b * C * p.HW + pix;
+        for (int j = 0; j < VEC; ++j) valid[j] = !((lab[j] < 0.f) || (lab[j] >= (float)C));  // mc_dropout.py:45
+    } else {
 #pragma unroll
-            for (int c = 0; c < C; ++c) {
-                float a[VEC];
-                unpack<VEC>(*reinterpret_cast<const F*>(sp + (size_t)c * p.HW), a);
-#pragma unroll
-                for (int j = 0; j < VEC; ++j) {
-                    const float pb = __fdiv_rn(a[j], Tf);
-                    pe[j] = pe[j] - pb * log2f(pb + kEps);
-                    top2[j] = fmaxf(top2[j], fminf(top1[j], pb));
-                    top1[j] = fmaxf(top1[j], pb);
-                }
-            }
-            float se[VEC];
-            unpack<VEC>(*reinterpret_cast<const F*>(p.sum_ent + (size_t)b * p.HW + pix), se);
-#pragma unroll
-            for (int j = 0; j < VEC; ++j) {
-                const float ee = __fdiv_rn(se[j], Tf);
-                sc[DAS_SCORE_PRED_ENTROPY][j] = valid[j] ? pe[j] : 0.f;
-                sc[DAS_SCORE_EXPECTED_ENTROPY][j] = valid[j] ? ee : 0.f;
-                sc[DAS_SCORE_BALD][j] = valid[j] ? pe[j] - ee : 0.f;
-                sc[DAS_SCORE_CONFIDENCE][j] = valid[j] ? top1[j] : 1.f;
-                sc[DAS_SCORE_MARGIN][j] = valid[j] ? top1[j] - top2[j] : 1.f;
-            }
-            const size_t o = (size_t)b * p.HW + pix;
-            if (p.pred_entropy) *reinterpret_cast<F*>(p.pred_entropy + o) = pack<VEC>(sc[DAS_SCORE_PRED_ENTROPY]);
-            if (p.bald) *reinterpret_cast<F*>(p.bald + o) = pack<VEC>(sc[DAS_SCORE_BALD]);
-            if (p.confidence) *reinterpret_cast<F*>(p.confidence + o) = pack<VEC>(sc[DAS_SCORE_CONFIDENCE]);
-            if (p.margin) *reinterpret_cast<F*>(p.margin + o) = pack<VEC>(sc[DAS_SCORE_MARGIN]);
-        }
+        for (int j = 0; j < VEC; ++j) valid[j] = true;
+    }
+}
 
-        if (VOTES) {
-            const uint8_t* vp = p.votes + (size_t)b * p.T_cap * p.HW + pix;
-            constexpr int U = 4;
-            for (int t0 = 0; t0 < p.T; t0 += U) {
-                uint32_t w[U];
+// predictive entropy / confidence / margin of p_bar = sum_p / T with the reference's formulas
+// (ceal.py:36,84-90,116-118); BALD = pred_entropy - sum_ent / T; masking as mc_dropout.py:49, ceal.py:39,91
+template <int C, int VEC, typename GetAcc>
+__device__ __forceinline__ void probs_scores(GetAcc get_acc, const float* ent, float Tf, const bool* valid,
+                                             float (*sc)[VEC]) {
+    float pe[VEC], top1[VEC], top2[VEC];
 #pragma unroll
-                for (int u = 0; u < U; ++u) {
-                    const int t = t0 + u;
-                    if (t < p.T) {
-                        if (VEC == 4)
-                            w[u] = *reinterpret_cast<const uint32_t*>(vp + (size_t)t * p.HW);
-                        else
-                            w[u] = vp[(size_t)t * p.HW];
-                    }
-                }
+    for (int j = 0; j < VEC; ++j) pe[j] = 0.f, top1[j] = -1.f, top2[j] = -1.f;
 #pragma unroll
-                for (int u = 0; u < U; ++u) {
-                    if (t0 + u < p.T) {
+    for (int c = 0; c < C; ++c) {
+        float a[VEC];
+        get_acc(c, a);
 #pragma unroll
-                        for (int j = 0; j < VEC; ++j) {
-                            const int v = (w[u] >> (8 * j)) & 0xff;
-                            hist8[(v * NT + tid) * VEC + j] += 1;
-                        }
-                    }
-                }
-                if (t0 == 0 && p.weak_labels) {  // vote of pass 0, 255 where invalid (ceal.py:157-163)
-                    uint32_t wl = 0;
-#pragma unroll
-                    for (int j = 0; j < VEC; ++j) wl |= (valid[j] ? ((w[0] >> (8 * j)) & 0xffu) : 255u) << (8 * j);
-                    uint8_t* wp = p.weak_labels + (size_t)b * p.HW + pix;
-                    if (VEC == 4)
-                        *reinterpret_cast<uint32_t*>(wp) = wl;
-                    else
-                        *wp = (uint8_t)wl;
-                }
-            }
-            float ve[VEC];
-#pragma unroll
-            for (int j = 0; j < VEC; ++j) ve[j] = 0.f;
-#pragma unroll
-            for (int c = 0; c < C; ++c) {
-                uint32_t w;
-                if (VEC == 4)
-                    w = hist32[c * NT + tid];
-                else
-                    w = hist8[c * NT + tid];
-#pragma unroll
-                for (int j = 0; j < VEC; ++j) ve[j] = ve[j] - lut[(w >> (8 * j)) & 0xff];
-            }
-#pragma unroll
-            for (int j = 0; j < VEC; ++j) sc[DAS_SCORE_VOTE_ENTROPY][j] = valid[j] ? ve[j] : 0.f;
-            if (p.vote_entropy)
-                *reinterpret_cast<F*>(p.vote_entropy + (size_t)b * p.HW + pix) = pack<VEC>(sc[DAS_SCORE_VOTE_ENTROPY]);
+        for (int j = 0; j < VEC; ++j) {
+            const float pb = __fdiv_rn(a[j], Tf);
+            pe[j] = pe[j] - pb * log2f(pb + kEps);
+            top2[j] = fmaxf(top2[j], fminf(top1[j], pb));
+            top1[j] = fmaxf(top1[j], pb);
         }
     }
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) {
+        const float ee = __fdiv_rn(ent[j], Tf);
+        sc[DAS_SCORE_PRED_ENTROPY][j] = valid[j] ? pe[j] : 0.f;
+        sc[DAS_SCORE_EXPECTED_ENTROPY][j] = valid[j] ? ee : 0.f;
+        sc[DAS_SCORE_BALD][j] = valid[j] ? pe[j] - ee : 0.f;
+        sc[DAS_SCORE_CONFIDENCE][j] = valid[j] ? top1[j] : 1.f;
+        sc[DAS_SCORE_MARGIN][j] = valid[j] ? top1[j] - top2[j] : 1.f;
+    }
+}
 
-    // image pooling: thread -> warp shuffle -> shared memory -> one partial row per block
+template <int VEC>
+__device__ __forceinline__ void store_maps(const McFinParams& f, size_t map_off, float (*sc)[VEC], bool probs,
+                                           bool votes) {
+    using F = typename VecT<VEC>::F;
+    if (probs) {
+        if (f.pred_entropy) *reinterpret_cast<F*>(f.pred_entropy + map_off) = pack<VEC>(sc[DAS_SCORE_PRED_ENTROPY]);
+        if (f.bald) *reinterpret_cast<F*>(f.bald + map_off) = pack<VEC>(sc[DAS_SCORE_BALD]);
+        if (f.confidence) *reinterpret_cast<F*>(f.confidence + map_off) = pack<VEC>(sc[DAS_SCORE_CONFIDENCE]);
+        if (f.margin) *reinterpret_cast<F*>(f.margin + map_off) = pack<VEC>(sc[DAS_SCORE_MARGIN]);
+    }
+    if (votes && f.vote_entropy)
+        *reinterpret_cast<F*>(f.vote_entropy + map_off) = pack<VEC>(sc[DAS_SCORE_VOTE_ENTROPY]);
+}
+
+// vote of pass 0, 255 where invalid (ceal.py:157-163)
+template <int VEC>
+__device__ __forceinline__ void store_weak_labels(uint8_t* weak_labels, size_t map_off, uint32_t first_vote,
+                                                  const bool* valid) {
+    uint32_t wl = 0;
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) wl |= (valid[j] ? ((first_vote >> (8 * j)) & 0xffu) : 255u) << (8 * j);
+    store_bytes<VEC>(weak_labels + map_off, wl);
+}
+
+// image pooling: thread -> warp shuffle -> shared memory -> one partial row per block (fixed order)
+template <int VEC, int NT>
+__device__ __forceinline__ void block_partials(float (*sc)[VEC], float (*red)[NT / 32], float* partials_row, int tid) {
     const int lane = tid & 31, wid = tid >> 5;
 #pragma unroll
     for (int k = 0; k < DAS_N_SCORES; ++k) {
@@ -328,17 +383,156 @@ __global__ void __launch_bounds__(kFinalizeThreads) mc_finalize_kernel(const McF
         float s = 0.f;
 #pragma unroll
         for (int w = 0; w < NT / 32; ++w) s += red[tid][w];
-        p.partials[((size_t)b * p.blocks_per_image + blockIdx.x) * DAS_N_SCORES + tid] = s;
+        partials_row[tid] = s;
     }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K2: state -> per-pixel maps + per-block partial sums of every score.
+// ---------------------------------------------------------------------------------------------
+template <int C, int VEC, bool PROBS, bool VOTES>
+__global__ void __launch_bounds__(kFinalizeThreads) mc_finalize_kernel(const McFinParams p) {
+    using F = typename VecT<VEC>::F;
+    constexpr int NT = kFinalizeThreads;
+    __shared__ uint32_t hist32[VOTES ? C * NT * VEC / 4 : 1];
+    __shared__ float lut[VOTES ? 256 : 1];
+    __shared__ float red[DAS_N_SCORES][NT / 32];
+    uint8_t* hist8 = reinterpret_cast<uint8_t*>(hist32);
+
+    const int tid = threadIdx.x;
+    const int b = blockIdx.y;
+    const long long pix = ((long long)blockIdx.x * NT + tid) * VEC;
+    const bool active = pix < p.HW;
+    if (VOTES) hist_setup<C, VEC, NT>(hist8, lut, p.T, tid);
+
+    float sc[DAS_N_SCORES][VEC];
+#pragma unroll
+    for (int k = 0; k < DAS_N_SCORES; ++k)
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) sc[k][j] = 0.f;
+
+    if (active) {
+        const size_t map_off = (size_t)b * p.HW + pix;
+        bool valid[VEC];
+        load_valid<C, VEC>(p.labels, map_off, valid);
+        if (PROBS) {
+            const float* sp = p.sum_p + (size_t)b * C * p.HW + pix;
+            float se[VEC];
+            unpack<VEC>(*reinterpret_cast<const F*>(p.sum_ent + map_off), se);
+            probs_scores<C, VEC>([&](int c, float* a) { unpack<VEC>(*reinterpret_cast<const F*>(sp + (size_t)c * p.HW), a); },
+                                 se, (float)p.T, valid, sc);
+        }
+        if (VOTES) {
+            const uint8_t* vp = p.votes + (size_t)b * p.T_cap * p.HW + pix;
+            uint32_t first_vote = 0;
+            constexpr int U = 4;
+            for (int t0 = 0; t0 < p.T; t0 += U) {
+                uint32_t w[U];
+#pragma unroll
+                for (int u = 0; u < U; ++u)
+                    if (t0 + u < p.T) w[u] = load_bytes<VEC>(vp + (size_t)(t0 + u) * p.HW);
+#pragma unroll
+                for (int u = 0; u < U; ++u)
+                    if (t0 + u < p.T) hist_add<VEC, NT>(hist8, w[u], tid);
+                if (t0 == 0) first_vote = w[0];
+            }
+            float ve[VEC];
+            hist_vote_entropy<C, VEC, NT>(hist8, lut, tid, ve);
+#pragma unroll
+            for (int j = 0; j < VEC; ++j) sc[DAS_SCORE_VOTE_ENTROPY][j] = valid[j] ? ve[j] : 0.f;
+            if (p.weak_labels) store_weak_labels<VEC>(p.weak_labels, map_off, first_vote, valid);
+        }
+        store_maps<VEC>(p, map_off, sc, PROBS, VOTES);
+    }
+    block_partials<VEC, NT>(sc, red, p.partials + ((size_t)b * p.blocks_per_image + blockIdx.x) * DAS_N_SCORES, tid);
+}
+
+// ---------------------------------------------------------------------------------------------
+// K1+K2 fused, for the LAST pass group of a batch: the group's logits are consumed exactly as in K1, but
+// the accumulators never go back to HBM - the finalize arithmetic of K2 runs on them directly and only
+// maps / block partials are written.  With pass_begin == 0 (all T passes in one group, T <= 32) no state is
+// read or written at all: HBM traffic == the logits, once.  Votes go straight into the per-thread
+// shared-memory histogram (votes of earlier groups are re-read from the state).
+// ---------------------------------------------------------------------------------------------
+template <int C, int VEC, bool PROBS, bool VOTES, bool SMEM, int MINB>
+__global__ void __launch_bounds__(kAccThreads, MINB) mc_score_kernel(const McScoreParams q) {
+    using F = typename VecT<VEC>::F;
+    constexpr int NT = kAccThreads;
+    const McAccParams& p = q.acc;
+    const McFinParams& f = q.fin;
+    extern __shared__ float4 acc_smem[];
+    __shared__ uint32_t hist32[VOTES ? C * NT * VEC / 4 + 1 : 1];
+    __shared__ float lut[VOTES ? 256 : 1];
+    __shared__ float red[DAS_N_SCORES][NT / 32];
+    uint8_t* hist8 = reinterpret_cast<uint8_t*>(hist32);
+
+    const int tid = threadIdx.x;
+    const int b = blockIdx.y;
+    const long long pix = ((long long)blockIdx.x * NT + tid) * VEC;
+    const bool active = pix < p.HW;
+    if (VOTES) hist_setup<C, VEC, NT>(hist8, lut, f.T, tid);
+
+    float sc[DAS_N_SCORES][VEC];
+#pragma unroll
+    for (int k = 0; k < DAS_N_SCORES; ++k)
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) sc[k][j] = 0.f;
+
+    if (active) {
+        const size_t img_off = (size_t)b * C * p.HW + pix;
+        const size_t map_off = (size_t)b * p.HW + pix;
+        const uint64_t pol_stream = policy_evict_first();
+
+        Acc<C, VEC, SMEM> acc;
+        acc.s = reinterpret_cast<F*>(acc_smem) + tid;
+        float ent[VEC];
+        uint32_t first_vote = 0;
+        if (PROBS) mc_acc_init<C, VEC, SMEM>(acc, ent, p.pass_begin == 0, p.sum_p, p.sum_ent, img_off, map_off, p.HW);
+        if (VOTES) {  // votes recorded by earlier groups of this batch
+            const uint8_t* vp = p.votes + (size_t)b * p.T_cap * p.HW + pix;
+            for (int t = 0; t < p.pass_begin; ++t) {
+                const uint32_t w = load_bytes<VEC>(vp + (size_t)t * p.HW);
+                if (t == 0) first_vote = w;
+                hist_add<VEC, NT>(hist8, w, tid);
+            }
+        }
+
+        for (int g = 0; g < p.n_passes; ++g) {
+            const uint32_t vote_word = mc_pass<C, VEC, PROBS, VOTES, SMEM>(p.logits[g] + img_off, p.HW, pol_stream, acc, ent);
+            if (VOTES) {
+                hist_add<VEC, NT>(hist8, vote_word, tid);
+                if (g == 0 && p.pass_begin == 0) first_vote = vote_word;
+                if (p.votes != nullptr)  // keep the recorded votes complete (absent in single-shot states)
+                    store_bytes<VEC>(p.votes + ((size_t)b * p.T_cap + (p.pass_begin + g)) * p.HW + pix, vote_word);
+            }
+        }
+
+        // ---- finalize straight from the accumulators (same arithmetic as mc_finalize_kernel) ----
+        bool valid[VEC];
+        load_valid<C, VEC>(f.labels, map_off, valid);
+        if (PROBS) probs_scores<C, VEC>([&](int c, float* a) { acc.get(c, a); }, ent, (float)f.T, valid, sc);
+        if (VOTES) {
+            float ve[VEC];
+            hist_vote_entropy<C, VEC, NT>(hist8, lut, tid, ve);
+#pragma unroll
+            for (int j = 0; j < VEC; ++j) sc[DAS_SCORE_VOTE_ENTROPY][j] = valid[j] ? ve[j] : 0.f;
+            if (f.weak_labels) store_weak_labels<VEC>(f.weak_labels, map_off, first_vote, valid);
+        }
+        store_maps<VEC>(f, map_off, sc, PROBS, VOTES);
+    }
+    block_partials<VEC, NT>(sc, red, f.partials + ((size_t)b * f.blocks_per_image + blockIdx.x) * DAS_N_SCORES, tid);
 }
 
 // per-class-count launchers (instantiated in mc_inst.cu for a range of C)
 template <int C>
-int launch_accumulate(const McAccParams& p, int B, bool vec4, int flags, cudaStream_t st);
+int launch_accumulate(const McAccParams& p, int B, int vec, int flags, cudaStream_t st);
 template <int C>
-int launch_finalize(const McFinParams& p, int B, bool vec4, int flags, cudaStream_t st);
+int launch_finalize(const McFinParams& p, int B, int vec, int flags, cudaStream_t st);
+template <int C>
+int launch_score(const McScoreParams& p, int B, int vec, int flags, cudaStream_t st);
 
-int dispatch_accumulate(const McAccParams& p, int B, bool vec4, int flags, cudaStream_t st);
-int dispatch_finalize(const McFinParams& p, int B, bool vec4, int flags, cudaStream_t st);
+int dispatch_accumulate(const McAccParams& p, int B, int vec, int flags, cudaStream_t st);
+int dispatch_finalize(const McFinParams& p, int B, int vec, int flags, cudaStream_t st);
+int dispatch_score(const McScoreParams& p, int B, int vec, int flags, cudaStream_t st);
 
 }  // namespace das

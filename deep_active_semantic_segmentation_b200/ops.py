@@ -13,7 +13,7 @@ from typing import Iterable, Sequence
 import torch
 
 from . import _lib
-from ._lib import MC_PROBS, MC_VOTES, N_SCORES, SCORE_INDEX, DasError, McDesc, check
+from ._lib import MC_PROBS, MC_SINGLE_SHOT, MC_VOTES, N_SCORES, SCORE_INDEX, DasError, McDesc, check
 
 MAP_NAMES = ("vote_entropy", "pred_entropy", "bald", "confidence", "margin")
 
@@ -43,9 +43,13 @@ class MCState:
     """
 
     def __init__(self, B: int, C_: int, H: int, W: int, T_cap: int, votes: bool = True, probs: bool = True,
-                 device=None):
+                 device=None, single_shot: bool = False):
+        """single_shot: all T_cap (<= 32) passes will arrive in one score() call - the state then holds
+        only the per-block partial sums (no accumulators, no votes)."""
         self.lib = _lib.load()
-        self.desc = McDesc(B, C_, H, W, T_cap, (MC_VOTES if votes else 0) | (MC_PROBS if probs else 0))
+        self.single_shot = single_shot
+        self.desc = McDesc(B, C_, H, W, T_cap, (MC_VOTES if votes else 0) | (MC_PROBS if probs else 0)
+                           | (MC_SINGLE_SHOT if single_shot else 0))
         self.B, self.C, self.H, self.W, self.T_cap = B, C_, H, W, T_cap
         self.votes, self.probs = votes, probs
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
@@ -63,15 +67,37 @@ class MCState:
         group = [pass_logits] if isinstance(pass_logits, torch.Tensor) else list(pass_logits)
         start = 0
         while start < len(group):
-            chunk = [_need_cuda(t, "logits", torch.float32) for t in group[start:start + _lib.MAX_PASS_GROUP]]
-            for t in chunk:
-                if tuple(t.shape) != (self.B, self.C, self.H, self.W):
-                    raise DasError(f"logits shape {tuple(t.shape)} != {(self.B, self.C, self.H, self.W)}")
+            chunk = self._check_group(group[start:start + _lib.MAX_PASS_GROUP])
             arr = (C.c_void_p * len(chunk))(*[t.data_ptr() for t in chunk])
             check(self.lib.das_mc_accumulate(C.byref(self.desc), _ptr(self.state), arr, len(chunk), self.n_passes,
                                              _stream()), "das_mc_accumulate")
             self.n_passes += len(chunk)
             start += len(chunk)
+
+    def _check_group(self, pass_logits):
+        group = [pass_logits] if isinstance(pass_logits, torch.Tensor) else list(pass_logits)
+        chunk = [_need_cuda(t, "logits", torch.float32) for t in group]
+        for t in chunk:
+            if tuple(t.shape) != (self.B, self.C, self.H, self.W):
+                raise DasError(f"logits shape {tuple(t.shape)} != {(self.B, self.C, self.H, self.W)}")
+        return chunk
+
+    def score(self, pass_logits, labels: torch.Tensor | None, maps: Iterable[str] = (), scores: bool = True,
+              weak_labels: bool = False, scores_out: torch.Tensor | None = None) -> dict:
+        """Fused K1+K2 on the LAST group of passes (das_mc_accumulate_finalize): earlier groups, if any,
+        went through accumulate(); with none (the whole MC stack in one call) no state touches HBM."""
+        chunk = self._check_group(pass_logits)
+        if len(chunk) > _lib.MAX_PASS_GROUP:     # leading passes through the streaming kernel
+            head = len(chunk) - _lib.MAX_PASS_GROUP
+            self.accumulate(chunk[:head])
+            chunk = chunk[head:]
+        labels, bufs, wl, sc = self._outputs(labels, maps, scores, weak_labels, scores_out)
+        arr = (C.c_void_p * len(chunk))(*[t.data_ptr() for t in chunk])
+        check(self.lib.das_mc_accumulate_finalize(C.byref(self.desc), _ptr(self.state), arr, len(chunk), self.n_passes,
+                                                  _ptr(labels), *[_ptr(bufs.get(n)) for n in MAP_NAMES], _ptr(wl),
+                                                  _ptr(sc), _stream()), "das_mc_accumulate_finalize")
+        self.n_passes += len(chunk)
+        return self._pack(bufs, wl, sc)
 
     def finalize(self, labels: torch.Tensor | None, maps: Iterable[str] = (), scores: bool = True,
                  weak_labels: bool = False, scores_out: torch.Tensor | None = None) -> dict:
@@ -79,11 +105,17 @@ class MCState:
         scores_out: optional contiguous f32 [B,6] destination (e.g. a slice of a pool-wide score table)."""
         if self.n_passes < 1:
             raise DasError("finalize() before any accumulate()")
+        labels, bufs, wl, sc = self._outputs(labels, maps, scores, weak_labels, scores_out)
+        check(self.lib.das_mc_finalize(C.byref(self.desc), _ptr(self.state), _ptr(labels), self.n_passes,
+                                       *[_ptr(bufs.get(n)) for n in MAP_NAMES], _ptr(wl), _ptr(sc), _stream()),
+              "das_mc_finalize")
+        return self._pack(bufs, wl, sc)
+
+    def _outputs(self, labels, maps, scores, weak_labels, scores_out):
         if labels is not None:
             labels = _need_cuda(labels, "labels", torch.float32)
             if tuple(labels.shape) != (self.B, self.H, self.W):
                 raise DasError(f"labels shape {tuple(labels.shape)} != {(self.B, self.H, self.W)}")
-        out = {}
         bufs = {}
         for name in maps:
             if name not in MAP_NAMES:
@@ -97,10 +129,11 @@ class MCState:
             sc = scores_out
         else:
             sc = torch.empty((self.B, N_SCORES), dtype=torch.float32, device=self.device) if scores else None
-        check(self.lib.das_mc_finalize(C.byref(self.desc), _ptr(self.state), _ptr(labels), self.n_passes,
-                                       *[_ptr(bufs.get(n)) for n in MAP_NAMES], _ptr(wl), _ptr(sc), _stream()),
-              "das_mc_finalize")
-        out.update(bufs)
+        return labels, bufs, wl, sc
+
+    @staticmethod
+    def _pack(bufs, wl, sc):
+        out = dict(bufs)
         if wl is not None:
             out["weak_labels"] = wl
         if sc is not None:

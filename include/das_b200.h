@@ -62,8 +62,10 @@ uint64_t das_launch_count(void);
 
 enum {
     DAS_MC_VOTES = 1,  /* keep the per-pass argmax votes   -> vote entropy (reference-pinned)   */
-    DAS_MC_PROBS = 2   /* keep running sum of softmax probabilities and of per-pass entropies   */
+    DAS_MC_PROBS = 2,  /* keep running sum of softmax probabilities and of per-pass entropies   */
                        /* -> predictive entropy, BALD, confidence, margin, expected entropy     */
+    DAS_MC_SINGLE_SHOT = 4 /* all T (<= DAS_MAX_PASS_GROUP) passes arrive in ONE                */
+                       /* das_mc_accumulate_finalize call: the state holds only block partials  */
 };
 
 /* order of the per-image scores written by das_mc_finalize */
@@ -82,7 +84,7 @@ typedef struct das_mc_desc {
     int32_t C;      /* classes, 2..DAS_MAX_CLASSES                           */
     int32_t H, W;   /* pixels                                                */
     int32_t T_cap;  /* passes the state can hold, 1..DAS_MAX_PASSES          */
-    int32_t flags;  /* DAS_MC_VOTES | DAS_MC_PROBS                           */
+    int32_t flags;  /* DAS_MC_VOTES | DAS_MC_PROBS [| DAS_MC_SINGLE_SHOT]    */
 } das_mc_desc;
 
 /* Size of the caller-allocated state for `desc` (256-byte aligned device buffer). Layout:
@@ -119,6 +121,17 @@ int das_mc_accumulate(const das_mc_desc* desc, void* state, const float* const* 
 int das_mc_finalize(const das_mc_desc* desc, void* state, const float* labels, int T,
                     float* vote_entropy, float* pred_entropy, float* bald, float* confidence,
                     float* margin, uint8_t* weak_labels, float* image_scores, void* stream);
+
+/* K1+K2 fused for the LAST pass group of a batch: consumes passes pass_begin .. pass_begin+n_passes-1
+ * like das_mc_accumulate, then finalises with T = pass_begin + n_passes like das_mc_finalize - but the
+ * accumulators stay in registers, the state is not written back.  With pass_begin == 0 (the whole
+ * Monte-Carlo stack of a batch in one group; required when DAS_MC_SINGLE_SHOT is set) no state is read
+ * or written at all: HBM traffic is the logits, once, plus the requested outputs.  Same outputs,
+ * same arithmetic and same fixed reduction order as the two-call form. */
+int das_mc_accumulate_finalize(const das_mc_desc* desc, void* state, const float* const* pass_logits,
+                               int n_passes, int pass_begin, const float* labels, float* vote_entropy,
+                               float* pred_entropy, float* bald, float* confidence, float* margin,
+                               uint8_t* weak_labels, float* image_scores, void* stream);
 
 /* Device pointer to the recorded votes, u8 [B,T_cap,H,W] (test / debugging aid). */
 int das_mc_votes_ptr(const das_mc_desc* desc, void* state, uint8_t** votes);

@@ -19,19 +19,30 @@ def _ops():
     return ops
 
 
-def run_gpu(logits, labels, group, votes=True, probs=True, weak=False):
-    """logits numpy [B,T,C,H,W] -> dict of numpy outputs from the CUDA path."""
+def run_gpu(logits, labels, group, votes=True, probs=True, weak=False, fused=False):
+    """logits numpy [B,T,C,H,W] -> dict of numpy outputs from the CUDA path.
+
+    fused=False: das_mc_accumulate per group, then das_mc_finalize (K1 ... K1, K2).
+    fused=True : das_mc_accumulate for all but the last group, das_mc_accumulate_finalize for the last one
+                 (single-shot state, i.e. no accumulators in HBM at all, when one group holds every pass)."""
     ops = _ops()
     B, T, C, H, W = logits.shape
-    st = ops.MCState(B, C, H, W, T, votes=votes, probs=probs)
+    single = fused and group >= T and T <= 32
+    st = ops.MCState(B, C, H, W, T, votes=votes, probs=probs, single_shot=single)
     dev = [torch.from_numpy(np.ascontiguousarray(logits[:, t])).cuda() for t in range(T)]
-    for t0 in range(0, T, group):
-        st.accumulate(dev[t0:t0 + group])
     maps = (["vote_entropy"] if votes else []) + ([m for m in ops.MAP_NAMES if m != "vote_entropy"] if probs else [])
     lab = None if labels is None else torch.from_numpy(labels).cuda()
-    out = st.finalize(lab, maps=maps, scores=True, weak_labels=weak and votes)
+    groups = [dev[t0:t0 + group] for t0 in range(0, T, group)]
+    if fused:
+        for g in groups[:-1]:
+            st.accumulate(g)
+        out = st.score(groups[-1], lab, maps=maps, scores=True, weak_labels=weak and votes)
+    else:
+        for g in groups:
+            st.accumulate(g)
+        out = st.finalize(lab, maps=maps, scores=True, weak_labels=weak and votes)
     res = {k: v.cpu().numpy() for k, v in out.items()}
-    if votes:
+    if votes and not single:
         res["votes"] = st.votes_tensor().cpu().numpy()
     torch.cuda.synchronize()
     return res
@@ -44,7 +55,8 @@ def check_against_oracle(res, logits, labels, votes=True, probs=True):
         o = R.mc_maps(logits[b], None if labels is None else labels[b], C)
         osc = R.image_scores(o)
         if votes:
-            np.testing.assert_array_equal(res["votes"][b, :T], o["votes"])            # index work: bit exact
+            if "votes" in res:
+                np.testing.assert_array_equal(res["votes"][b, :T], o["votes"])        # index work: bit exact
             np.testing.assert_allclose(res["vote_entropy"][b], o["vote_entropy"], rtol=RTOL, atol=ATOL_MAP)
             np.testing.assert_allclose(res["scores"][b, SCORE_INDEX["vote_entropy"]], osc["vote_entropy"], rtol=RTOL, atol=ATOL_SCORE)
         else:
@@ -74,20 +86,23 @@ CASES = [
 
 @pytest.mark.parametrize("B,T,C,H,W,block", CASES)
 @pytest.mark.parametrize("group", [1, 3, 64])
-def test_mc_matches_oracle(B, T, C, H, W, block, group):
+@pytest.mark.parametrize("fused", [False, True])
+def test_mc_matches_oracle(B, T, C, H, W, block, group, fused):
     gs = list(range(B))
     logits = synth.pool_logits(7, gs, T, C, H, W, block)
     labels = synth.pool_labels(7, gs, H, W, C, block)
-    res = run_gpu(logits, labels, min(group, T))
+    res = run_gpu(logits, labels, min(group, T), fused=fused)
     check_against_oracle(res, logits, labels)
 
 
 def test_mc_votes_only_and_probs_only_and_no_labels():
     logits = synth.pool_logits(9, [0, 1], 6, 19, 20, 28, 4)
     labels = synth.pool_labels(9, [0, 1], 20, 28, 19, 4)
-    check_against_oracle(run_gpu(logits, labels, 2, votes=True, probs=False), logits, labels, True, False)
-    check_against_oracle(run_gpu(logits, labels, 2, votes=False, probs=True), logits, labels, False, True)
-    check_against_oracle(run_gpu(logits, None, 6), logits, None)
+    for fused in (False, True):
+        check_against_oracle(run_gpu(logits, labels, 2, votes=True, probs=False, fused=fused), logits, labels, True, False)
+        check_against_oracle(run_gpu(logits, labels, 2, votes=False, probs=True, fused=fused), logits, labels, False, True)
+        check_against_oracle(run_gpu(logits, None, 6, fused=fused), logits, None)
+        check_against_oracle(run_gpu(logits, labels, 6, votes=True, probs=False, fused=fused), logits, labels, True, False)
 
 
 def test_mc_exact_ties_pick_first_class_and_labels_edge_values():
@@ -97,12 +112,14 @@ def test_mc_exact_ties_pick_first_class_and_labels_edge_values():
     logits[0, 1, 5] = 2.0                                       # tie between 3 and 5 -> 3
     labels = np.zeros((B, H, W), dtype=np.float32)
     labels[0, 0, :] = [-1, -0.0, 6, 6.5, 7, 255, np.nan, 3]     # valid iff not (l<0 or l>=C); NaN stays valid
-    res = run_gpu(logits, labels, 3, weak=True)
-    check_against_oracle(res, logits, labels)
-    assert (res["votes"][0, 0] == 0).all() and (res["votes"][0, 1] == 3).all()
     wl = R.votes_from_logits(logits[0, 0]).copy()
     wl[~R.valid_mask(labels[0], C)] = 255
-    np.testing.assert_array_equal(res["weak_labels"][0], wl)
+    for fused, group in ((False, 3), (True, 3), (True, 2)):
+        res = run_gpu(logits, labels, group, weak=True, fused=fused)
+        check_against_oracle(res, logits, labels)
+        if "votes" in res:
+            assert (res["votes"][0, 0] == 0).all() and (res["votes"][0, 1] == 3).all()
+        np.testing.assert_array_equal(res["weak_labels"][0], wl)
 
 
 def test_mc_extreme_logits():
@@ -139,6 +156,14 @@ def test_full_size_properties():
     assert torch.equal(votes, votes_g)
     for k in list(ops.MAP_NAMES) + ["scores"]:
         assert torch.equal(out[k], out_g[k]), k
+    # the fused last-group kernel (single shot, and after a streamed head) gives bit-identical results
+    for group in (20, 8):
+        st = ops.MCState(B, C, H, W, T, single_shot=(group == 20))
+        for t0 in range(0, T - group, group):
+            st.accumulate(passes[t0:t0 + group])
+        out_f = st.score(passes[T - (T % group or group):], lab, maps=ops.MAP_NAMES, scores=True)
+        for k in list(ops.MAP_NAMES) + ["scores"]:
+            assert torch.equal(out[k], out_f[k]), (group, k)
     # vote entropy is invariant under a permutation of the passes (histogram), bit for bit
     perm = list(np.random.default_rng(0).permutation(T))
     out_p, _ = run(perm, 4)
@@ -178,3 +203,8 @@ def test_errors_are_loud():
     st.accumulate([torch.zeros(1, 5, 8, 8, device="cuda")] * 2)
     with pytest.raises(DasError):
         st.accumulate(torch.zeros(1, 5, 8, 8, device="cuda"))   # state is full (T_cap = 2)
+    single = ops.MCState(1, 5, 8, 8, 2, single_shot=True)
+    with pytest.raises(DasError):
+        single.accumulate(torch.zeros(1, 5, 8, 8, device="cuda"))   # a single-shot state has no accumulators
+    with pytest.raises(DasError):
+        ops.MCState(1, 5, 8, 8, 33, single_shot=True)               # more passes than one launch can take

@@ -30,15 +30,15 @@ def main():
     for B in (1, 2, 4, 8):
         passes, labels = synth.device_pass_logits(1, 0, B, T, C, H, W, dev)
         for votes, probs in ((True, True), (True, False)):
-            st = ops.MCState(B, C, H, W, T, votes=votes, probs=probs, device=dev)
             for G in (1, 2, 4, 5, 10, 20):
+                st = ops.MCState(B, C, H, W, T, votes=votes, probs=probs, device=dev, single_shot=(G >= T))
                 groups = [passes[t0:t0 + G] for t0 in range(0, T, G)]
 
                 def step():
                     st.reset()
-                    for g in groups:
+                    for g in groups[:-1]:
                         st.accumulate(g)
-                    st.finalize(labels, maps=())
+                    st.score(groups[-1], labels, maps=())
 
                 for _ in range(3):
                     step()
@@ -55,7 +55,7 @@ def main():
                 a0.record()
                 for _ in range(iters):
                     st.reset()
-                    for g in groups:
+                    for g in groups[:-1]:
                         st.accumulate(g)
                 a1.record()
                 torch.cuda.synchronize()
