@@ -46,6 +46,9 @@ def parse():
     ap.add_argument("--pass-group", type=int, default=int(os.environ.get("DAS_BENCH_PASS_GROUP", 20)))
     ap.add_argument("--e2e-steps", type=int, default=6)
     ap.add_argument("--e2e-batch", type=int, default=2)
+    ap.add_argument("--mode", default="full", choices=["full", "votes", "probs"],
+                    help="full = vote entropy + softmax scores (default); votes = the reference's vote entropy only; "
+                         "probs = softmax-mean entropy / BALD / confidence / margin only")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
@@ -157,7 +160,8 @@ def run_b200(args):
     # synthetic pool slice, resident in HBM: T pass buffers of [B,C,H,W] (+ labels); every step re-reads
     # T*B*C*H*W*4 bytes (6.4 GB at B=8) >> 126 MB L2, so the logits always come from HBM
     passes, labels = synth.device_pass_logits(synth.DEFAULT_SEED, rank * K * B, B, T, C, H, W, dev)
-    state = ops.MCState(B, C, H, W, T, votes=True, probs=True, device=dev, single_shot=(G >= T))
+    votes, probs = args.mode in ("full", "votes"), args.mode in ("full", "probs")
+    state = ops.MCState(B, C, H, W, T, votes=votes, probs=probs, device=dev, single_shot=(G >= T))
     pool_scores = torch.zeros((K * B, _lib.N_SCORES), dtype=torch.float32, device=dev)
     groups = [passes[t0:t0 + G] for t0 in range(0, T, G)]
     acc_events, fin_events = [], []
@@ -180,7 +184,7 @@ def run_b200(args):
                 (fin_events if last else acc_events).append((e0, e1, len(grp)))
 
     def select():
-        col = pool_scores[:, SCORE_INDEX["bald"]].contiguous()
+        col = pool_scores[:, SCORE_INDEX["bald" if probs else "vote_entropy"]].contiguous()
         s, i = ops.topk(col, min(TOPK, col.numel()), True)
         if world > 1:
             cs, ci = dist.gather_candidates(s, i + rank * K * B, TOPK)
@@ -225,7 +229,7 @@ def run_b200(args):
                 traffic = tj.get("dram_bytes_per_launch")
         except Exception:
             traffic = None
-    kname = "mc_score_kernel<C=19,VEC=4,probs,votes> (fused K1+K2)" if G >= T else "mc_accumulate_kernel / mc_score_kernel <C=19,VEC=4,probs,votes>"
+    kname = "mc_score_kernel<C=19,VEC=2> (fused K1+K2)" if G >= T else "mc_accumulate_kernel / mc_score_kernel <C=19,VEC=2>"
     roofline = {"bound": "hbm", "kernel": kname, "achieved": round(achieved, 1),
                 "peak": peaks["hbm_gbs"], "peak_kind": peak_kind + " copy bandwidth (burst)", "unit": "GB/s",
                 "frac": round(achieved / peaks["hbm_gbs"], 4), "traffic": traffic,
@@ -243,7 +247,9 @@ def run_b200(args):
             "ms_per_step": round(elapsed_ms / K, 4), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "pool_images": POOL_IMAGES, "H": H, "W": W, "classes": C, "mc_passes": T,
-                       "batch_images_per_step": B, "pass_group": G, "topk": TOPK, "scores": "vote_entropy+pred_entropy+bald+confidence+margin",
+                       "batch_images_per_step": B, "pass_group": G, "topk": TOPK, "mode": args.mode,
+                       "scores": {"full": "vote_entropy+pred_entropy+bald+confidence+margin", "votes": "vote_entropy",
+                                  "probs": "pred_entropy+bald+confidence+margin"}[args.mode],
                        "sharding": f"by image, {world} rank(s), candidate all-gather only",
                        "l2": f"inputs {T * B * C * H * W * 4 / 1e9:.2f} GB per step >> 126 MB L2 (no flush needed)"},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,

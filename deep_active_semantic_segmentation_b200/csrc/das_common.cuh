@@ -63,51 +63,58 @@ __device__ __forceinline__ float ex2_approx(float x) {
     return y;
 }
 
-// L2 cache policies: logits are touched once (evict-first); running state should survive in
-// the 126 MB L2 between the launches of consecutive passes (evict-last).
-__device__ __forceinline__ uint64_t policy_evict_first() {
-    uint64_t p;
-    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
-    return p;
+// Blackwell packed fp32: one FFMA2 / FADD2 / FMUL2 issue slot does two IEEE fp32 operations (lane-wise, same
+// rounding as the scalar instructions).  The kernels that own pixel PAIRS use them to halve the issue
+// slots of the softmax arithmetic.
+struct __align__(8) f32x2 {
+    float x, y;
+};
+__device__ __forceinline__ unsigned long long pk(f32x2 a) {
+    unsigned long long r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a.x), "f"(a.y));
+    return r;
 }
-__device__ __forceinline__ uint64_t policy_evict_last() {
-    uint64_t p;
-    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
-    return p;
+__device__ __forceinline__ f32x2 upk(unsigned long long v) {
+    f32x2 r;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(v));
+    return r;
+}
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+    unsigned long long d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(pk(a)), "l"(pk(b)), "l"(pk(c)));
+    return upk(d);
+}
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) {
+    unsigned long long d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(pk(a)), "l"(pk(b)));
+    return upk(d);
+}
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
+    unsigned long long d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(pk(a)), "l"(pk(b)));
+    return upk(d);
 }
 
-// streaming 128-bit / 32-bit loads: read-only path, no L1 allocation, L2 policy hint
-__device__ __forceinline__ float4 ldg_stream(const float4* p, uint64_t pol) {
+// Streaming loads of the logits: read-only path, no L1 allocation (each logit is used exactly once).
+// An L2 evict-first policy (createpolicy + .L2::cache_hint) was measured and dropped: the policy descriptor
+// has to be moved into a uniform register pair for every load (2 extra R2UR per LDG), and with the fused
+// single-shot kernel nothing else competes for L2 anyway (profiles/r1_k1_notes.md).
+__device__ __forceinline__ float4 ldg_stream(const float4* p) {
     float4 v;
-    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.f32 {%0,%1,%2,%3}, [%4], %5;"
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
                  : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
-                 : "l"(p), "l"(pol));
+                 : "l"(p));
     return v;
 }
-__device__ __forceinline__ float ldg_stream(const float* p, uint64_t pol) {
+__device__ __forceinline__ float2 ldg_stream(const float2* p) {
+    float2 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.f32 {%0,%1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ float ldg_stream(const float* p) {
     float v;
-    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(v) : "l"(p), "l"(pol));
+    asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));
     return v;
-}
-__device__ __forceinline__ float4 ldg_hint(const float4* p, uint64_t pol) {
-    float4 v;
-    asm volatile("ld.global.L2::cache_hint.v4.f32 {%0,%1,%2,%3}, [%4], %5;"
-                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
-                 : "l"(p), "l"(pol));
-    return v;
-}
-__device__ __forceinline__ float ldg_hint(const float* p, uint64_t pol) {
-    float v;
-    asm volatile("ld.global.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(v) : "l"(p), "l"(pol));
-    return v;
-}
-__device__ __forceinline__ void stg_hint(float4* p, float4 v, uint64_t pol) {
-    asm volatile("st.global.L2::cache_hint.v4.f32 [%0], {%1,%2,%3,%4}, %5;" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z),
-                 "f"(v.w), "l"(pol)
-                 : "memory");
-}
-__device__ __forceinline__ void stg_hint(float* p, float v, uint64_t pol) {
-    asm volatile("st.global.L2::cache_hint.f32 [%0], %1, %2;" ::"l"(p), "f"(v), "l"(pol) : "memory");
 }
 
 template <typename T>

@@ -56,6 +56,8 @@ int mc_validate(const das_mc_desc* d) {
     if ((d->flags & DAS_MC_SINGLE_SHOT) && d->T_cap > DAS_MAX_PASS_GROUP) return DAS_ERR_UNSUPPORTED;
     if (d->C < 2) return DAS_ERR_INVALID_ARG;
     if (d->C > DAS_MAX_CLASSES || d->T_cap > DAS_MAX_PASSES || d->B > 65535) return DAS_ERR_UNSUPPORTED;
+    // plane offsets inside one image are formed in 32 bits (c * H*W*4 bytes)
+    if ((unsigned long long)d->C * d->H * d->W * sizeof(float) >= (1ull << 32)) return DAS_ERR_UNSUPPORTED;
     return DAS_OK;
 }
 

@@ -9,9 +9,10 @@
 namespace das {
 
 // Kernel configuration (measured with tools/k1_bench.cu on B200, profiles/r1_k1_variants.txt):
-//   PROBS kernels, even H*W : VEC = 2 (64-bit loads), accumulators in shared memory, 5-8 blocks/SM
-//                             (0.87-0.93 of the measured HBM peak; VEC = 4 needs 160-240 registers and
-//                             stays at 0.60-0.77 because only 8-12 warps fit)
+//   PROBS kernels, even H*W : VEC = 2 (64-bit loads).  C <= 20: accumulators in registers, 128 regs, 4 blocks/SM
+//                             (best under the sustained power cap: 0.83 of the measured HBM peak, 0.92 in a
+//                             burst); C > 20: accumulators in shared memory, 4-6 blocks/SM (0.80-0.82 / 0.95).
+//                             VEC = 4 needs 160-255 registers and stays at 0.79 / 0.80-0.90.
 //   PROBS kernels, odd  H*W : VEC = 1 (class planes are mutually misaligned), accumulators in registers
 //   vote-only kernels       : VEC = 4 / 1, everything in registers (already at the copy roofline)
 // static + dynamic shared memory can exceed the 48 KB default limit -> always opt in.
@@ -41,8 +42,13 @@ int launch_accumulate(const McAccParams& p, int B, int vec, int flags, cudaStrea
     } while (0)
     if (probs) {
         if (vec == 2) {
-            if (votes) DAS_ACC(2, true, true, true, minb_vec2(C), smem2);
-            else DAS_ACC(2, true, false, true, minb_vec2(C), smem2);
+            if constexpr (C <= 20) {
+                if (votes) DAS_ACC(2, true, true, false, 4, 0);
+                else DAS_ACC(2, true, false, false, 4, 0);
+            } else {
+                if (votes) DAS_ACC(2, true, true, true, minb_vec2(C), smem2);
+                else DAS_ACC(2, true, false, true, minb_vec2(C), smem2);
+            }
         } else if (vec == 1) {
             if (votes) DAS_ACC(1, true, true, false, minb_vec1(C), 0);
             else DAS_ACC(1, true, false, false, minb_vec1(C), 0);
@@ -90,8 +96,13 @@ int launch_score(const McScoreParams& p, int B, int vec, int flags, cudaStream_t
     } while (0)
     if (probs) {
         if (vec == 2) {
-            if (votes) DAS_SCORE(2, true, true, true, minb_vec2(C), smem2);
-            else DAS_SCORE(2, true, false, true, minb_vec2(C), smem2);
+            if constexpr (C <= 20) {
+                if (votes) DAS_SCORE(2, true, true, false, 4, 0);
+                else DAS_SCORE(2, true, false, false, 4, 0);
+            } else {
+                if (votes) DAS_SCORE(2, true, true, true, minb_vec2(C), smem2);
+                else DAS_SCORE(2, true, false, true, minb_vec2(C), smem2);
+            }
         } else if (vec == 1) {
             if (votes) DAS_SCORE(1, true, true, false, minb_vec1(C), 0);
             else DAS_SCORE(1, true, false, false, minb_vec1(C), 0);

@@ -1,7 +1,7 @@
 // K1 (streaming softmax/argmax -> accumulate), K2 (finalize + image pooling) and the fused K1+K2 kernel.
 //
 // Data layout in HBM (all per batch of B images, HW = H*W pixels):
-//   logits   f32 [B,C,HW]      one buffer per Monte-Carlo pass, read exactly once (evict-first)
+//   logits   f32 [B,C,HW]      one buffer per Monte-Carlo pass, read exactly once (no L1 allocation)
 //   sum_p    f32 [B,C,HW]      running sum_t softmax(x_t)            (same layout as the logits)
 //   sum_ent  f32 [B,HW]        running sum_t entropy(softmax(x_t))
 //   votes    u8  [B,T_cap,HW]  argmax of every pass (the reference's outputs[B,T,H,W], as bytes)
@@ -94,22 +94,8 @@ __device__ __forceinline__ float pack<1>(const float* in) {
 }
 
 template <int VEC>
-__device__ __forceinline__ typename VecT<VEC>::F ldg_stream_v(const float* p, uint64_t pol);
-template <>
-__device__ __forceinline__ float4 ldg_stream_v<4>(const float* p, uint64_t pol) {
-    return ldg_stream(reinterpret_cast<const float4*>(p), pol);
-}
-template <>
-__device__ __forceinline__ float2 ldg_stream_v<2>(const float* p, uint64_t pol) {
-    float2 v;
-    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v2.f32 {%0,%1}, [%2], %3;"
-                 : "=f"(v.x), "=f"(v.y)
-                 : "l"(p), "l"(pol));
-    return v;
-}
-template <>
-__device__ __forceinline__ float ldg_stream_v<1>(const float* p, uint64_t pol) {
-    return ldg_stream(p, pol);
+__device__ __forceinline__ typename VecT<VEC>::F ldg_stream_v(const float* p) {
+    return ldg_stream(reinterpret_cast<const typename VecT<VEC>::F*>(p));
 }
 
 // VEC bytes (one per pixel) <-> memory
@@ -163,47 +149,89 @@ constexpr size_t acc_smem_bytes(int C, int VEC) { return (size_t)C * kAccThreads
 //     (log-sum-exp form of ceal.py:118: one log2 per pixel instead of one per logit; it differs from
 //      the reference's "+1e-12" form by < 2e-12 per class and has no cancellation, both terms >= 0)
 template <int C, int VEC, bool PROBS, bool VOTES, bool SMEM>
-__device__ __forceinline__ uint32_t mc_pass(const float* __restrict__ xp, long long HW, uint64_t pol,
+__device__ __forceinline__ uint32_t mc_pass(const float* __restrict__ xp, uint32_t plane_bytes,
                                             Acc<C, VEC, SMEM>& acc, float* ent) {
     float x[C][VEC];
+    // plane c of this image lives plane_bytes*c further on: one IMAD.WIDE per address
+    const char* xb = reinterpret_cast<const char*>(xp);
 #pragma unroll
-    for (int c = 0; c < C; ++c) unpack<VEC>(ldg_stream_v<VEC>(xp + (size_t)c * HW, pol), x[c]);
+    for (int c = 0; c < C; ++c)
+        unpack<VEC>(ldg_stream_v<VEC>(reinterpret_cast<const float*>(xb + (size_t)((uint32_t)c * plane_bytes))), x[c]);
     uint32_t vote_word = 0;
     float inv[VEC];
+    float m[VEC];
 #pragma unroll
     for (int j = 0; j < VEC; ++j) {
-        float m = x[0][j];
+        m[j] = x[0][j];
 #pragma unroll
-        for (int c = 1; c < C; ++c) m = fmaxf(m, x[c][j]);
+        for (int c = 1; c < C; ++c) m[j] = fmaxf(m[j], x[c][j]);
         if (VOTES) {
             int v = 0;
 #pragma unroll
-            for (int c = C - 1; c >= 0; --c) v = (x[c][j] == m) ? c : v;  // first max wins
+            for (int c = C - 1; c >= 0; --c) v = (x[c][j] == m[j]) ? c : v;  // first max wins
             vote_word |= (uint32_t)v << (8 * j);
-        }
-        if (PROBS) {
-            const float mL = m * kLog2e;
-            float s = 0.f, a = 0.f;
-#pragma unroll
-            for (int c = 0; c < C; ++c) {
-                const float y = fmaf(x[c][j], kLog2e, -mL);
-                const float e = ex2_approx(y);
-                s += e;
-                a = fmaf(e, y, a);
-                x[c][j] = e;
-            }
-            inv[j] = __frcp_rn(s);
-            ent[j] += log2f(s) - a * inv[j];
         }
     }
     if (PROBS) {
+        if constexpr (VEC % 2 == 0) {
+            // pixel pairs through the packed fp32 pipe (FFMA2 / FADD2): same per-lane IEEE arithmetic as below
 #pragma unroll
-        for (int c = 0; c < C; ++c) {
-            float a[VEC];
-            acc.get(c, a);
+            for (int h = 0; h < VEC / 2; ++h) {
+                const int j0 = 2 * h, j1 = 2 * h + 1;
+                const f32x2 L2 = {kLog2e, kLog2e};
+                const f32x2 nmL = {-(m[j0] * kLog2e), -(m[j1] * kLog2e)};
+                f32x2 s = {0.f, 0.f}, a = {0.f, 0.f};
 #pragma unroll
-            for (int j = 0; j < VEC; ++j) a[j] = fmaf(x[c][j], inv[j], a[j]);
-            acc.set(c, a);
+                for (int c = 0; c < C; ++c) {
+                    const f32x2 y = fma2(f32x2{x[c][j0], x[c][j1]}, L2, nmL);
+                    const f32x2 e = {ex2_approx(y.x), ex2_approx(y.y)};
+                    s = add2(s, e);
+                    a = fma2(e, y, a);
+                    x[c][j0] = e.x;
+                    x[c][j1] = e.y;
+                }
+                inv[j0] = __frcp_rn(s.x);
+                inv[j1] = __frcp_rn(s.y);
+                ent[j0] += log2f(s.x) - a.x * inv[j0];
+                ent[j1] += log2f(s.y) - a.y * inv[j1];
+            }
+#pragma unroll
+            for (int c = 0; c < C; ++c) {
+                float av[VEC];
+                acc.get(c, av);
+#pragma unroll
+                for (int h = 0; h < VEC / 2; ++h) {
+                    const f32x2 r = fma2(f32x2{x[c][2 * h], x[c][2 * h + 1]}, f32x2{inv[2 * h], inv[2 * h + 1]},
+                                         f32x2{av[2 * h], av[2 * h + 1]});
+                    av[2 * h] = r.x;
+                    av[2 * h + 1] = r.y;
+                }
+                acc.set(c, av);
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < VEC; ++j) {
+                const float mL = m[j] * kLog2e;
+                float s = 0.f, a = 0.f;
+#pragma unroll
+                for (int c = 0; c < C; ++c) {
+                    const float y = fmaf(x[c][j], kLog2e, -mL);
+                    const float e = ex2_approx(y);
+                    s += e;
+                    a = fmaf(e, y, a);
+                    x[c][j] = e;
+                }
+                inv[j] = __frcp_rn(s);
+                ent[j] += log2f(s) - a * inv[j];
+            }
+#pragma unroll
+            for (int c = 0; c < C; ++c) {
+                float av[VEC];
+                acc.get(c, av);
+#pragma unroll
+                for (int j = 0; j < VEC; ++j) av[j] = fmaf(x[c][j], inv[j], av[j]);
+                acc.set(c, av);
+            }
         }
     }
     return vote_word;
@@ -242,15 +270,15 @@ __global__ void __launch_bounds__(kAccThreads, MINB) mc_accumulate_kernel(const 
     const int b = blockIdx.y;
     const size_t img_off = (size_t)b * C * p.HW + pix;
     const size_t map_off = (size_t)b * p.HW + pix;
-    const uint64_t pol_stream = policy_evict_first();
 
+    const uint32_t plane_bytes = (uint32_t)(p.HW * sizeof(float));  // C * plane_bytes < 4 GB is validated on the host
     Acc<C, VEC, SMEM> acc;
     acc.s = reinterpret_cast<F*>(acc_smem) + threadIdx.x;
     float ent[VEC];
     if (PROBS) mc_acc_init<C, VEC, SMEM>(acc, ent, p.pass_begin == 0, p.sum_p, p.sum_ent, img_off, map_off, p.HW);
 
     for (int g = 0; g < p.n_passes; ++g) {
-        const uint32_t vote_word = mc_pass<C, VEC, PROBS, VOTES, SMEM>(p.logits[g] + img_off, p.HW, pol_stream, acc, ent);
+        const uint32_t vote_word = mc_pass<C, VEC, PROBS, VOTES, SMEM>(p.logits[g] + img_off, plane_bytes, acc, ent);
         if (VOTES) store_bytes<VEC>(p.votes + ((size_t)b * p.T_cap + (p.pass_begin + g)) * p.HW + pix, vote_word);
     }
 
@@ -316,6 +344,9 @@ __device__ __forceinline__ void load_valid(const float* labels, size_t map_off, 
 template <int C, int VEC, typename GetAcc>
 __device__ __forceinline__ void probs_scores(GetAcc get_acc, const float* ent, float Tf, const bool* valid,
                                              float (*sc)[VEC]) {
+    // mean over passes as a multiplication by fl(1/T): exact for T = 1 (the reference-pinned CEAL case) and for
+    // power-of-two T, otherwise within one float32 ulp of the division the composed oracle uses
+    const float invT = __frcp_rn(Tf);
     float pe[VEC], top1[VEC], top2[VEC];
 #pragma unroll
     for (int j = 0; j < VEC; ++j) pe[j] = 0.f, top1[j] = -1.f, top2[j] = -1.f;
@@ -325,7 +356,7 @@ __device__ __forceinline__ void probs_scores(GetAcc get_acc, const float* ent, f
         get_acc(c, a);
 #pragma unroll
         for (int j = 0; j < VEC; ++j) {
-            const float pb = __fdiv_rn(a[j], Tf);
+            const float pb = a[j] * invT;
             pe[j] = pe[j] - pb * log2f(pb + kEps);
             top2[j] = fmaxf(top2[j], fminf(top1[j], pb));
             top1[j] = fmaxf(top1[j], pb);
@@ -333,7 +364,7 @@ __device__ __forceinline__ void probs_scores(GetAcc get_acc, const float* ent, f
     }
 #pragma unroll
     for (int j = 0; j < VEC; ++j) {
-        const float ee = __fdiv_rn(ent[j], Tf);
+        const float ee = ent[j] * invT;
         sc[DAS_SCORE_PRED_ENTROPY][j] = valid[j] ? pe[j] : 0.f;
         sc[DAS_SCORE_EXPECTED_ENTROPY][j] = valid[j] ? ee : 0.f;
         sc[DAS_SCORE_BALD][j] = valid[j] ? pe[j] - ee : 0.f;
@@ -481,8 +512,8 @@ __global__ void __launch_bounds__(kAccThreads, MINB) mc_score_kernel(const McSco
     if (active) {
         const size_t img_off = (size_t)b * C * p.HW + pix;
         const size_t map_off = (size_t)b * p.HW + pix;
-        const uint64_t pol_stream = policy_evict_first();
-
+    
+        const uint32_t plane_bytes = (uint32_t)(p.HW * sizeof(float));
         Acc<C, VEC, SMEM> acc;
         acc.s = reinterpret_cast<F*>(acc_smem) + tid;
         float ent[VEC];
@@ -498,7 +529,7 @@ __global__ void __launch_bounds__(kAccThreads, MINB) mc_score_kernel(const McSco
         }
 
         for (int g = 0; g < p.n_passes; ++g) {
-            const uint32_t vote_word = mc_pass<C, VEC, PROBS, VOTES, SMEM>(p.logits[g] + img_off, p.HW, pol_stream, acc, ent);
+            const uint32_t vote_word = mc_pass<C, VEC, PROBS, VOTES, SMEM>(p.logits[g] + img_off, plane_bytes, acc, ent);
             if (VOTES) {
                 hist_add<VEC, NT>(hist8, vote_word, tid);
                 if (g == 0 && p.pass_begin == 0) first_vote = vote_word;
