@@ -44,13 +44,13 @@ def main():
         if "--stalls" in sys.argv:
             st = []
             for i, h in enumerate(hdr):
-                if h.startswith(STALL_PREFIX) and h.endswith("_per_warp_active.pct"):
+                if h.startswith(STALL_PREFIX) and h.endswith("_per_issue_active.ratio"):
                     try:
-                        st.append((float(r[i]), h[len(STALL_PREFIX):-len("_per_warp_active.pct")]))
+                        st.append((float(r[i]), h[len(STALL_PREFIX):-len("_per_issue_active.ratio")]))
                     except ValueError:
                         pass
-            for v, n in sorted(st, reverse=True)[:6]:
-                print(f"   stall {n:28s} {v:.1f} %")
+            for v, n in sorted(st, reverse=True)[:7]:
+                print(f"   stalled warps per issue: {n:22s} {v:.2f}")
         print()
 
 
