@@ -11,6 +11,7 @@ import os
 PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(PKG, "libdas_b200.so")
 
+ABI_VERSION = 2
 MC_VOTES = 1
 MC_PROBS = 2
 MC_SINGLE_SHOT = 4
@@ -53,10 +54,13 @@ _PROTOTYPES = {
     "das_nms_sequences": (_i, [_vp, _i, _i, _i, _i, _i, _f, _vp, _vp, _vp, _vp]),
     "das_topk_workspace_bytes": (_i, [_i, _i, C.POINTER(_sz)]),
     "das_topk": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp]),
-    "das_kcenter_init": (_i, [_vp, _i, _i, _i, _i, _vp, _i, _vp, _vp, _vp]),
-    "das_kcenter_step": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
+    "das_kcenter_filter_bytes": (_i, [_i, _i, _i, C.POINTER(_sz)]),
+    "das_kcenter_filter_build": (_i, [_vp, _i, _i, _i, _i, _vp, _vp]),
+    "das_kcenter_filter_stats": (_i, [_vp, _i, _i, _i, C.POINTER(C.c_uint64), _vp]),
+    "das_kcenter_init": (_i, [_vp, _i, _i, _i, _i, _vp, _i, _vp, _vp, _vp, _vp]),
+    "das_kcenter_step": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
     "das_kcenter_workspace_bytes": (_i, [_i, _i, C.POINTER(_sz)]),
-    "das_kcenter_greedy": (_i, [_vp, _i, _i, _vp, _i, _i, _vp, _vp, _vp, _vp]),
+    "das_kcenter_greedy": (_i, [_vp, _i, _i, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp]),
 }
 EXPORTED_SYMBOLS = tuple(_PROTOTYPES)
 
@@ -79,8 +83,8 @@ def load(build_if_missing: bool = True):
         fn = getattr(lib, name)  # AttributeError here = the library does not match the header
         fn.restype = res
         fn.argtypes = args
-    if lib.das_abi_version() != 1:
-        raise DasError(f"libdas_b200 ABI {lib.das_abi_version()} != 1")
+    if lib.das_abi_version() != ABI_VERSION:
+        raise DasError(f"libdas_b200 ABI {lib.das_abi_version()} != {ABI_VERSION}")
     _lib = lib
     return lib
 

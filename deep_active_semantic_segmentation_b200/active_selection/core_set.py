@@ -19,6 +19,18 @@ class ActiveSelectionCoreSet(ActiveSelectionBase):
     def __init__(self, dataset_lmdb_env, crop_size, dataloader_batch_size):
         super(ActiveSelectionCoreSet, self).__init__(dataset_lmdb_env, crop_size, dataloader_batch_size)
         self.last_min_distances = None
+        #: tensor-core (tcgen05 bf16) distance filter in front of the exact float64 update: "auto" = when the
+        #: feature matrix is large enough to matter and the N x rows table fits in free HBM; True / False force it.
+        #: Selections are bit-identical either way.
+        self.tensor_core_filter = "auto"
+        self.last_filter_stats = None
+
+    def _make_filter(self, feats, lo, hi):
+        n, d = feats.shape
+        use = self.tensor_core_filter
+        if use == "auto":
+            use = n * d >= (1 << 20) and ops.kcenter_filter_budget_ok(n, d, hi - lo, feats.device)
+        return ops.KCenterFilter(feats, lo, hi) if use else None
 
     @staticmethod
     def _as_device_features(features):
@@ -44,8 +56,10 @@ class ActiveSelectionCoreSet(ActiveSelectionBase):
             raise ValueError("k-center needs at least one already selected row (core_set.py:19)")
         W, rank = dist.world()
         if W == 1:
-            picks, min_d = ops.kcenter_greedy(feats, selected, N)
+            flt = self._make_filter(feats, 0, feats.shape[0])
+            picks, min_d = ops.kcenter_greedy(feats, selected, N, flt)
             picks = picks.cpu().tolist()
+            self.last_filter_stats = flt.stats() if flt is not None else None
         else:
             picks, min_d = self._select_batch_sharded(feats, selected, N, W, rank)
         self.last_min_distances = min_d
@@ -70,7 +84,8 @@ class ActiveSelectionCoreSet(ActiveSelectionBase):
         key = torch.zeros(2, dtype=torch.int64, device=dev)
         centre = torch.zeros(1, dtype=torch.int32, device=dev)
         cen = torch.as_tensor(selected, dtype=torch.int32, device=dev)
-        ops.kcenter_init(feats, lo, hi, cen, min_d2, key)
+        flt = self._make_filter(feats, lo, hi)
+        ops.kcenter_init(feats, lo, hi, cen, min_d2, key, flt)
         picks = []
         keys = [torch.empty_like(key) for _ in range(W)]
         for _ in range(N):
@@ -80,10 +95,11 @@ class ActiveSelectionCoreSet(ActiveSelectionBase):
             row = torch.where(allk[:, 0] == best, allk[:, 1], torch.full_like(allk[:, 1], 2 ** 62)).min()
             centre.copy_(row.to(torch.int32).reshape(1))
             picks.append(row)
-            ops.kcenter_step(feats, lo, hi, centre, min_d2, key)
+            ops.kcenter_step(feats, lo, hi, centre, min_d2, key, flt)
         parts = [torch.empty(dist.shard_bounds(n, W, r)[1] - dist.shard_bounds(n, W, r)[0], dtype=torch.float64, device=dev)
                  for r in range(W)]
         td.all_gather(parts, min_d2)
+        self.last_filter_stats = flt.stats() if flt is not None else None
         return [int(p) for p in torch.stack(picks).cpu().tolist()] if picks else [], torch.cat(parts).sqrt()
 
     def _pooled_features(self, model, combined_paths):

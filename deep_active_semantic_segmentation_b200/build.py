@@ -33,7 +33,7 @@ MC_RANGES = [(2, 9), (10, 16), (17, 20), (21, 24), (25, 28), (29, 32)]
 
 def _units():
     units = []
-    for name in ("mc_api", "region", "topk", "kcenter"):
+    for name in ("mc_api", "region", "topk", "kcenter", "gram"):
         units.append((name, os.path.join(CSRC, name + ".cu"), []))
     for lo, hi in MC_RANGES:
         units.append((f"mc_inst_{lo}_{hi}", os.path.join(CSRC, "mc_inst.cu"), [f"-DDAS_C_LO={lo}", f"-DDAS_C_HI={hi}"]))
@@ -87,7 +87,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
         results = list(ex.map(compile_one, _units()))
     objs = [o for o, _ in results]
     rebuilt = any(changed for _, changed in results)
-    if rebuilt or not os.path.exists(LIB) or force:
+    stale = os.path.exists(LIB) and any(os.path.getmtime(o) > os.path.getmtime(LIB) for o in objs)
+    if rebuilt or stale or not os.path.exists(LIB) or force:
         cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB] + objs + ["-lcudart"]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:

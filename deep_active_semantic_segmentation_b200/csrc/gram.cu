@@ -1,0 +1,356 @@
+// K4, tensor-core part: pairwise squared distances of the core-set features on the 5th-generation tensor
+// cores (tcgen05.mma, BF16 operands staged by TMA, FP32 accumulators in TMEM), fused with the distance
+// epilogue  d2~[c,i] = |f_i|^2 + |f_c|^2 - 2 <f_i, f_c>.
+//
+// Role in the k-center greedy (reference active_selection/core_set.py:17-38): the reference evaluates
+// sklearn float64 distances of every pool row to every new centre.  Here the BF16 tensor-core distances
+// are a FILTER with a proven error bound: a row's float64 min-distance can only change when
+//      d2~(i,c) - delta * (|f_i|^2 + |f_c|^2)  <=  min_d2[i],
+// and only those rows (a few per cent) are re-evaluated exactly in float64 (kcenter.cu).  Selections are
+// therefore identical to the exact float64 path; the tensor cores remove ~97 % of its work.
+//
+// Error bound: bf16 round-to-nearest has relative error <= 2^-9 per operand, so every product is within
+// 2^-8 (1 + 2^-10) of the exact one and, by Cauchy-Schwarz, |<a,b>~ - <a,b>| <= 2^-8 |a||b| + fp32
+// accumulation error (<= K * 2^-24 |a||b| = 2^-13 |a||b| for K = 2048).  With 2|a||b| <= |a|^2 + |b|^2 the
+// distance error is <= (2^-8 + 2^-13 + eps_f32) (|a|^2 + |b|^2); kFilterDelta = 2^-7 doubles that.
+//
+// Kernel anatomy (one CTA per SM, persistent over 128 x 256 output tiles):
+//   warp 0   TMA producer: 4-stage ring of {A 128x64, B 256x64} bf16 tiles, 128-byte swizzle
+//   warp 1   MMA issuer: one elected lane issues tcgen05.mma.cta_group::1.kind::f16 (M128 N256 K16)
+//   warp 2   TMEM allocator (512 columns = two 128x256 fp32 accumulators, double buffered)
+//   warps 4-7 epilogue: tcgen05.ld 32x32b -> registers -> distance -> coalesced stores of the TRANSPOSED
+//            tile (out[c, i], i fastest), overlapped with the next tile's main loop
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <math.h>
+
+#include "das_common.cuh"
+#include "gram.cuh"
+
+namespace das {
+
+constexpr int kBM = 128, kBN = 256, kBK = 64;  // tile; kBK bf16 = one 128-byte swizzle row
+constexpr int kStages = 4;
+constexpr int kUmmaK = 16;
+constexpr uint32_t kABytes = kBM * kBK * 2, kBBytes = kBN * kBK * 2, kStageBytes = kABytes + kBBytes;
+constexpr int kGemmThreads = 256;
+constexpr uint32_t kTmemCols = 512;
+
+// ---- PTX wrappers ---------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra WAIT_DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "WAIT_DONE:\n\t"
+        "}\n" ::"r"(bar),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+        "l"(map), "r"(bar), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}\n" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+        : "memory");
+}
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t* v) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// shared-memory matrix descriptor, K-major operand tile written by TMA with CU_TENSOR_MAP_SWIZZLE_128B:
+// rows are 128 bytes, 8-row groups are 1024 bytes apart (SBO), version 1 (Blackwell), layout SWIZZLE_128B
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3ffffu) >> 4);  // start address, 16-byte units
+    d |= (uint64_t)1 << 16;                    // leading byte offset (unused for swizzled K-major), 1
+    d |= (uint64_t)(1024 >> 4) << 32;          // stride byte offset: 8 rows * 128 B
+    d |= (uint64_t)1 << 46;                    // descriptor version
+    d |= (uint64_t)2 << 61;                    // SWIZZLE_128B
+    return d;
+}
+// instruction descriptor: D = f32, A = B = bf16, both K-major, M = 128, N = 256
+constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kBN >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24);
+
+// out[c * ld + i] = nrmA[i] + nrmB[c] - 2 <A_i, B_c>   for i < M (rows of A), c < Nn (rows of B)
+__global__ void __launch_bounds__(kGemmThreads, 1)
+    kc_dist_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                        const float* __restrict__ nrmA, const float* __restrict__ nrmB, float* __restrict__ out, int M,
+                        int Nn, int ld, int num_kb) {
+    extern __shared__ uint8_t smem_raw[];
+    // 1024-byte alignment for the 128-byte swizzle atoms
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* smem_al = smem_raw + (smem_base - smem_u32(smem_raw));
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_al + kStages * kStageBytes);
+    // bars[0..S) full, [S..2S) empty, [2S..2S+2) tmem_full, [2S+2..2S+4) tmem_empty
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
+    const uint32_t bar0 = smem_u32(bars);
+    auto full_bar = [&](int s) { return bar0 + 8u * s; };
+    auto empty_bar = [&](int s) { return bar0 + 8u * (kStages + s); };
+    auto tfull_bar = [&](int b) { return bar0 + 8u * (2 * kStages + b); };
+    auto tempty_bar = [&](int b) { return bar0 + 8u * (2 * kStages + 2 + b); };
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tiles_m = (M + kBM - 1) / kBM, tiles_n = (Nn + kBN - 1) / kBN;
+    const int tiles = tiles_m * tiles_n;
+
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < kStages; ++s) mbar_init(full_bar(s), 1), mbar_init(empty_bar(s), 1);
+        for (int b = 0; b < 2; ++b) mbar_init(tfull_bar(b), 1), mbar_init(tempty_bar(b), 4);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                     "r"(kTmemCols)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // ===== TMA producer =====
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int t = blockIdx.x; t < tiles; t += gridDim.x) {
+                const int tm = t % tiles_m, tn = t / tiles_m;
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    mbar_wait(empty_bar(stage), phase ^ 1u);
+                    const uint32_t sa = smem_base + stage * kStageBytes, sb = sa + kABytes;
+                    mbar_expect_tx(full_bar(stage), kStageBytes);
+                    tma_load_2d(sa, &tmA, full_bar(stage), kb * kBK, tm * kBM);
+                    tma_load_2d(sb, &tmB, full_bar(stage), kb * kBK, tn * kBN);
+                    if (++stage == kStages) stage = 0, phase ^= 1u;
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            // ===== MMA issuer =====
+            int stage = 0;
+            uint32_t phase = 0;
+            int it = 0;
+            for (int t = blockIdx.x; t < tiles; t += gridDim.x, ++it) {
+                const int buf = it & 1;
+                const uint32_t aphase = (uint32_t)(it >> 1) & 1u;
+                mbar_wait(tempty_bar(buf), aphase ^ 1u);  // epilogue has drained this accumulator
+                tc_fence_after();
+                const uint32_t tmem_d = tmem_base + (uint32_t)buf * kBN;
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    mbar_wait(full_bar(stage), phase);
+                    tc_fence_after();
+                    const uint32_t sa = smem_base + stage * kStageBytes, sb = sa + kABytes;
+                    const uint64_t adesc = umma_desc_sw128(sa), bdesc = umma_desc_sw128(sb);
+#pragma unroll
+                    for (int k = 0; k < kBK / kUmmaK; ++k) {
+                        // advance 16 bf16 = 32 bytes inside the swizzle row: +2 in 16-byte address units
+                        tc_mma_bf16(tmem_d, adesc + 2u * k, bdesc + 2u * k, kIdesc, (kb | k) != 0 ? 1u : 0u);
+                    }
+                    tc_commit(empty_bar(stage));  // frees the smem stage when these MMAs retire
+                    if (++stage == kStages) stage = 0, phase ^= 1u;
+                }
+                tc_commit(tfull_bar(buf));  // accumulator complete
+            }
+        }
+    } else if (warp >= 4) {
+        // ===== epilogue: TMEM -> registers -> distances -> transposed, coalesced stores =====
+        const int q = warp & 3;  // TMEM lane quarter this warp may access
+        int it = 0;
+        for (int t = blockIdx.x; t < tiles; t += gridDim.x, ++it) {
+            const int tm = t % tiles_m, tn = t / tiles_m;
+            const int buf = it & 1;
+            const uint32_t aphase = (uint32_t)(it >> 1) & 1u;
+            mbar_wait(tfull_bar(buf), aphase);
+            tc_fence_after();
+            const int i = tm * kBM + q * 32 + lane;  // row of A (fast index of the output)
+            const float na = i < M ? nrmA[i] : 0.f;
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)buf * kBN;
+#pragma unroll 1
+            for (int ch = 0; ch < kBN / 32; ++ch) {
+                uint32_t v[32];
+                tc_ld32(taddr + ch * 32, v);
+                tc_wait_ld();
+                const int c0 = tn * kBN + ch * 32;
+                if (c0 < Nn) {
+                    const float nbl = (c0 + lane) < Nn ? nrmB[c0 + lane] : 0.f;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const float nb = __shfl_sync(0xffffffffu, nbl, j);
+                        const int c = c0 + j;
+                        if (i < M && c < Nn) out[(size_t)c * ld + i] = fmaf(-2.f, __uint_as_float(v[j]), na + nb);
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty_bar(buf));
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+    }
+}
+
+// bf16 copy (zero padded to Dp), float64 and float32 squared norms: one warp per row
+__global__ void __launch_bounds__(256) kc_prepare_kernel(const float* __restrict__ feats, int N, int D, int Dp,
+                                                         __nv_bfloat16* __restrict__ fb, double* __restrict__ nrm64,
+                                                         float* __restrict__ nrm32) {
+    const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (row >= N) return;
+    const float* f = feats + (size_t)row * D;
+    __nv_bfloat16* o = fb + (size_t)row * Dp;
+    double s = 0.0;
+    for (int k = lane; k < Dp; k += 32) {
+        const float x = k < D ? f[k] : 0.f;
+        o[k] = __float2bfloat16_rn(x);
+        s = fma((double)x, (double)x, s);
+    }
+    s = warp_sum(s);
+    if (lane == 0) {
+        nrm64[row] = s;
+        nrm32[row] = (float)s;
+    }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_tiled_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (fn == nullptr) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+// bf16 [rows, Dp] row-major -> boxes of box_rows x 64 elements, 128-byte swizzle, zero fill out of bounds
+static int make_map(CUtensorMap* map, const __nv_bfloat16* base, int rows, int Dp, int box_rows) {
+    EncodeTiledFn enc = encode_tiled_fn();
+    if (enc == nullptr) return DAS_ERR_CUDA;
+    const cuuint64_t dims[2] = {(cuuint64_t)Dp, (cuuint64_t)rows};
+    const cuuint64_t strides[1] = {(cuuint64_t)Dp * sizeof(__nv_bfloat16)};
+    const cuuint32_t box[2] = {(cuuint32_t)kBK, (cuuint32_t)box_rows};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<__nv_bfloat16*>(base), dims, strides, box,
+                           estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                           CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        g_last_cuda_error = (int)r;
+        return DAS_ERR_CUDA;
+    }
+    return DAS_OK;
+}
+
+KcFilterLayout kc_filter_layout(int N, int D, int rows) {
+    KcFilterLayout L;
+    L.Dp = (D + kBK - 1) / kBK * kBK;
+    L.ld = (rows + 31) / 32 * 32;
+    size_t off = 0;
+    L.fb = off;
+    off += align_up((size_t)N * L.Dp * sizeof(__nv_bfloat16), 1024);
+    L.nrm64 = off;
+    off += align_up((size_t)N * sizeof(double), 256);
+    L.nrm32 = off;
+    off += align_up((size_t)N * sizeof(float), 256);
+    L.stats = off;
+    off += 256;
+    L.dt = off;
+    off += align_up((size_t)N * L.ld * sizeof(float), 256);
+    L.total = off;
+    return L;
+}
+
+constexpr size_t kGemmSmem = (size_t)kStages * kStageBytes + 1024 + 256;
+
+}  // namespace das
+
+using namespace das;
+
+extern "C" {
+
+int das_kcenter_filter_bytes(int N, int D, int rows, size_t* bytes) {
+    if (bytes == nullptr || N <= 0 || D <= 0 || rows <= 0 || rows > N) return DAS_ERR_INVALID_ARG;
+    *bytes = kc_filter_layout(N, D, rows).total;
+    return DAS_OK;
+}
+
+int das_kcenter_filter_build(const float* feats, int N, int D, int row_begin, int row_end, void* filter, void* stream) {
+    if (feats == nullptr || filter == nullptr) return DAS_ERR_INVALID_ARG;
+    if (N <= 0 || D <= 0 || row_begin < 0 || row_end > N || row_begin >= row_end) return DAS_ERR_INVALID_ARG;
+    if ((reinterpret_cast<uintptr_t>(filter) & 1023u) != 0) return DAS_ERR_MISALIGNED;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int rows = row_end - row_begin;
+    const KcFilterLayout L = kc_filter_layout(N, D, rows);
+    char* base = static_cast<char*>(filter);
+    __nv_bfloat16* fb = reinterpret_cast<__nv_bfloat16*>(base + L.fb);
+    double* nrm64 = reinterpret_cast<double*>(base + L.nrm64);
+    float* nrm32 = reinterpret_cast<float*>(base + L.nrm32);
+    float* dt = reinterpret_cast<float*>(base + L.dt);
+
+    DAS_CUDA(cudaMemsetAsync(base + L.stats, 0, 256, st));
+    DAS_LAUNCH(kc_prepare_kernel, (N + 7) / 8, 256, 0, st, feats, N, D, L.Dp, fb, nrm64, nrm32);
+    DAS_CHECK_LAUNCH();
+
+    CUtensorMap tmA, tmB;
+    int rc = make_map(&tmA, fb + (size_t)row_begin * L.Dp, rows, L.Dp, kBM);  // A: this rank's rows (fast output index)
+    if (rc != DAS_OK) return rc;
+    rc = make_map(&tmB, fb, N, L.Dp, kBN);  // B: every row (the candidate centres)
+    if (rc != DAS_OK) return rc;
+    DAS_CUDA(cudaFuncSetAttribute(kc_dist_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGemmSmem));
+    const int tiles = ((rows + kBM - 1) / kBM) * ((N + kBN - 1) / kBN);
+    const int grid = tiles < kNumSMs ? tiles : kNumSMs;
+    DAS_LAUNCH(kc_dist_gemm_kernel, grid, kGemmThreads, kGemmSmem, st, tmA, tmB, nrm32 + row_begin, nrm32, dt, rows, N,
+               L.ld, L.Dp / kBK);
+    DAS_CHECK_LAUNCH();
+    return DAS_OK;
+}
+
+}  // extern "C"

@@ -6,9 +6,14 @@
 // BASELINE size: 10k x 2048 x 4 B = 82 MB < 126 MB).  Every block leaves its best (value,row) in a small
 // table; the NEXT launch starts by reducing that table, so the greedy loop is a chain of launches with
 // no host round trip, no atomics and a deterministic tie rule.
+//
+// With a tensor-core distance filter (gram.cu, das_kcenter_filter_build) the launches screen every row with
+// its bf16 distance first and re-evaluate in float64 only the rows whose minimum can change; the values
+// written to min_d2 and the picks are bit-identical to the unfiltered path.
 #include <math.h>
 
 #include "das_common.cuh"
+#include "gram.cuh"
 
 namespace das {
 
@@ -117,6 +122,180 @@ __global__ void __launch_bounds__(kKcThreads) kcenter_kernel(const float* __rest
     }
 }
 
+
+// ---- tensor-core filtered variants --------------------------------------------------------------
+struct KcFilter {
+    const float* dt;            // [N, ld] screening distances, dt[c * ld + (row - row_begin)]
+    const double* nrm;          // [N] exact squared norms
+    unsigned long long* stats;  // [0] exact re-evaluations, [1] rows screened
+    int ld;
+};
+
+// arg-max of the previous launch's block table (every block computes the same answer)
+__device__ __forceinline__ int kc_table_argmax(const KcBest* __restrict__ prev_best, int n_prev, double* sv, int* si,
+                                               int* centre_s, int32_t* picks, int step) {
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    double bv = -1.0;
+    int bi = 0x7fffffff;
+    for (int i = tid; i < n_prev; i += kKcThreads) {
+        const KcBest q = prev_best[i];
+        if (q.idx >= 0 && kc_better(q.v, q.idx, bv, bi)) bv = q.v, bi = q.idx;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const double ov = __shfl_xor_sync(0xffffffffu, bv, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (kc_better(ov, oi, bv, bi)) bv = ov, bi = oi;
+    }
+    if (lane == 0) sv[wid] = bv, si[wid] = bi;
+    __syncthreads();
+    if (tid == 0) {
+        for (int w = 1; w < kKcWarps; ++w)
+            if (kc_better(sv[w], si[w], bv, bi)) bv = sv[w], bi = si[w];
+        *centre_s = bi;
+        if (blockIdx.x == 0 && picks != nullptr) picks[step] = bi;
+    }
+    __syncthreads();
+    const int c = *centre_s;
+    __syncthreads();
+    return c;
+}
+
+// Filtered init (core_set.py:19): one warp per row.  ub = min_l (d2~ + margin) bounds the true minimum from
+// above; only centres with d2~ - margin <= ub can attain it and are evaluated exactly.
+template <bool VEC4>
+__global__ void __launch_bounds__(kKcThreads) kcenter_finit_kernel(const float* __restrict__ feats, int D, int row_begin,
+                                                                   int row_end, const int32_t* __restrict__ centres, int L,
+                                                                   double* __restrict__ min_d2, KcBest* __restrict__ next_best,
+                                                                   const KcFilter f) {
+    __shared__ double sv[kKcWarps];
+    __shared__ int si[kKcWarps];
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    double bv = -1.0;
+    int bi = -1;
+    unsigned long long n_exact = 0;
+    for (int row = row_begin + blockIdx.x * kKcWarps + wid; row < row_end; row += gridDim.x * kKcWarps) {
+        const float* fr = feats + (size_t)row * D;
+        const double nr = f.nrm[row];
+        double ub = INFINITY;
+        for (int l = lane; l < L; l += 32) {
+            const int c = centres[l];
+            const double mg = kFilterDelta * (nr + f.nrm[c]);
+            ub = fmin(ub, (double)f.dt[(size_t)c * f.ld + (row - row_begin)] + mg);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) ub = fmin(ub, __shfl_xor_sync(0xffffffffu, ub, o));
+        double m = INFINITY;
+        for (int l0 = 0; l0 < L; l0 += 32) {
+            const int l = l0 + lane;
+            bool need = false;
+            if (l < L) {
+                const int c = centres[l];
+                const double mg = kFilterDelta * (nr + f.nrm[c]);
+                need = (double)f.dt[(size_t)c * f.ld + (row - row_begin)] - mg <= ub;
+            }
+            unsigned mask = __ballot_sync(0xffffffffu, need);
+            while (mask) {
+                const int j = __ffs(mask) - 1;
+                mask &= mask - 1;
+                m = fmin(m, warp_dist2<VEC4>(fr, feats + (size_t)centres[l0 + j] * D, D, lane));
+                ++n_exact;
+            }
+        }
+        if (lane == 0) min_d2[row - row_begin] = m;
+        if (bi < 0 || kc_better(m, row, bv, bi)) bv = m, bi = row;
+    }
+    if (lane == 0) sv[wid] = bv, si[wid] = bi;
+    __syncthreads();
+    if (tid == 0) {
+        for (int w = 1; w < kKcWarps; ++w)
+            if (si[w] >= 0 && (bi < 0 || kc_better(sv[w], si[w], bv, bi))) bv = sv[w], bi = si[w];
+        KcBest q;
+        q.v = bv, q.idx = bi, q.pad = 0;
+        next_best[blockIdx.x] = q;
+    }
+    if (lane == 0 && n_exact) atomicAdd(f.stats, n_exact);
+}
+
+// Filtered greedy step (core_set.py:26,37-38): one THREAD per row screens with the tensor-core distance;
+// rows that may change go to a shared-memory work list and are evaluated exactly by whole warps.
+template <bool VEC4, int MODE>
+__global__ void __launch_bounds__(kKcThreads) kcenter_fstep_kernel(const float* __restrict__ feats, int D, int row_begin,
+                                                                   int row_end, const int32_t* __restrict__ centres,
+                                                                   double* __restrict__ min_d2,
+                                                                   const KcBest* __restrict__ prev_best, int n_prev,
+                                                                   KcBest* __restrict__ next_best, int32_t* picks, int step,
+                                                                   const KcFilter f) {
+    __shared__ double sv[kKcWarps];
+    __shared__ int si[kKcWarps];
+    __shared__ int centre_s;
+    __shared__ int wl_row[kKcThreads];
+    __shared__ double wl_val[kKcThreads];
+    __shared__ int wl_n;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int centre = MODE == 1 ? centres[0] : kc_table_argmax(prev_best, n_prev, sv, si, &centre_s, picks, step);
+    const double nc = f.nrm[centre];
+    const float* fc = feats + (size_t)centre * D;
+    const float* dtc = f.dt + (size_t)centre * f.ld;
+
+    double bv = -1.0;
+    int bi = -1;
+    for (int base = row_begin + blockIdx.x * kKcThreads; base < row_end; base += gridDim.x * kKcThreads) {
+        if (tid == 0) wl_n = 0;
+        __syncthreads();
+        const int row = base + tid;
+        const bool in = row < row_end;
+        double m = 0.0;
+        bool need = false;
+        if (in) {
+            m = min_d2[row - row_begin];
+            need = (double)dtc[row - row_begin] - kFilterDelta * (f.nrm[row] + nc) <= m;
+        }
+        int slot = -1;
+        const unsigned mask = __ballot_sync(0xffffffffu, need);
+        if (mask) {
+            int wbase = 0;
+            if (lane == 0) wbase = atomicAdd(&wl_n, __popc(mask));
+            wbase = __shfl_sync(0xffffffffu, wbase, 0);
+            if (need) {
+                slot = wbase + __popc(mask & ((1u << lane) - 1u));
+                wl_row[slot] = row;
+            }
+        }
+        __syncthreads();
+        const int n_work = wl_n;
+        for (int k = wid; k < n_work; k += kKcWarps) {
+            const double d = warp_dist2<VEC4>(feats + (size_t)wl_row[k] * D, fc, D, lane);
+            if (lane == 0) wl_val[k] = d;
+        }
+        __syncthreads();
+        if (need) {
+            m = fmin(m, wl_val[slot]);
+            min_d2[row - row_begin] = m;
+        }
+        if (in && (bi < 0 || kc_better(m, row, bv, bi))) bv = m, bi = row;
+        if (tid == 0 && n_work) atomicAdd(f.stats, (unsigned long long)n_work);
+        __syncthreads();
+    }
+    // block arg-max
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const double ov = __shfl_xor_sync(0xffffffffu, bv, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (oi >= 0 && (bi < 0 || kc_better(ov, oi, bv, bi))) bv = ov, bi = oi;
+    }
+    if (lane == 0) sv[wid] = bv, si[wid] = bi;
+    __syncthreads();
+    if (tid == 0) {
+        for (int w = 1; w < kKcWarps; ++w)
+            if (si[w] >= 0 && (bi < 0 || kc_better(sv[w], si[w], bv, bi))) bv = sv[w], bi = si[w];
+        KcBest q;
+        q.v = bv, q.idx = bi, q.pad = 0;
+        next_best[blockIdx.x] = q;
+        if (blockIdx.x == 0) atomicAdd(f.stats + 1, (unsigned long long)(row_end - row_begin));
+    }
+}
+
 // reduce a block table to the packed pair key2 = {fp64 bits of the max, row index}
 __global__ void kcenter_key_kernel(const KcBest* best, int n, unsigned long long* key2, int32_t* picks, int step) {
     double bv = -1.0;
@@ -139,6 +318,12 @@ static int kc_grid(int rows) {
     const int cap = kNumSMs * 4;
     return want < cap ? (want < 1 ? 1 : want) : cap;
 }
+// filtered step: one thread per row
+static int kc_fgrid(int rows) {
+    const int want = (rows + kKcThreads - 1) / kKcThreads;
+    const int cap = kNumSMs * 4;
+    return want < cap ? (want < 1 ? 1 : want) : cap;
+}
 static bool kc_vec4(const float* feats, int D) { return D % 4 == 0 && aligned16(feats); }
 
 struct KcWorkspace {
@@ -156,6 +341,17 @@ static KcWorkspace kc_carve(void* ws, int N) {
     return w;
 }
 
+static KcFilter kc_filter_view(const void* filter, int N, int D, int rows) {
+    const KcFilterLayout L = kc_filter_layout(N, D, rows);
+    char* base = static_cast<char*>(const_cast<void*>(filter));
+    KcFilter f;
+    f.dt = reinterpret_cast<const float*>(base + L.dt);
+    f.nrm = reinterpret_cast<const double*>(base + L.nrm64);
+    f.stats = reinterpret_cast<unsigned long long*>(base + L.stats);
+    f.ld = L.ld;
+    return f;
+}
+
 template <int MODE>
 static int kc_launch(bool v4, int grid, cudaStream_t st, const float* feats, int D, int rb, int re, const int32_t* centres,
                      int L, double* min_d2, const KcBest* prev, int n_prev, KcBest* next, int32_t* picks, int step) {
@@ -165,6 +361,30 @@ static int kc_launch(bool v4, int grid, cudaStream_t st, const float* feats, int
     else
         DAS_LAUNCH((kcenter_kernel<false, MODE>), grid, kKcThreads, 0, st, feats, D, rb, re, centres, L, min_d2, prev,
                    n_prev, next, picks, step);
+    DAS_CHECK_LAUNCH();
+    return DAS_OK;
+}
+
+static int kc_launch_finit(bool v4, int grid, cudaStream_t st, const float* feats, int D, int rb, int re,
+                           const int32_t* centres, int L, double* min_d2, KcBest* next, const KcFilter& f) {
+    if (v4)
+        DAS_LAUNCH((kcenter_finit_kernel<true>), grid, kKcThreads, 0, st, feats, D, rb, re, centres, L, min_d2, next, f);
+    else
+        DAS_LAUNCH((kcenter_finit_kernel<false>), grid, kKcThreads, 0, st, feats, D, rb, re, centres, L, min_d2, next, f);
+    DAS_CHECK_LAUNCH();
+    return DAS_OK;
+}
+
+template <int MODE>
+static int kc_launch_fstep(bool v4, int grid, cudaStream_t st, const float* feats, int D, int rb, int re,
+                           const int32_t* centres, double* min_d2, const KcBest* prev, int n_prev, KcBest* next,
+                           int32_t* picks, int step, const KcFilter& f) {
+    if (v4)
+        DAS_LAUNCH((kcenter_fstep_kernel<true, MODE>), grid, kKcThreads, 0, st, feats, D, rb, re, centres, min_d2, prev,
+                   n_prev, next, picks, step, f);
+    else
+        DAS_LAUNCH((kcenter_fstep_kernel<false, MODE>), grid, kKcThreads, 0, st, feats, D, rb, re, centres, min_d2, prev,
+                   n_prev, next, picks, step, f);
     DAS_CHECK_LAUNCH();
     return DAS_OK;
 }
@@ -184,15 +404,19 @@ static int ensure_step_table() {
 extern "C" {
 
 int das_kcenter_init(const float* feats, int N, int D, int row_begin, int row_end, const int32_t* centers, int L,
-                     double* min_d2, unsigned long long* key2, void* stream) {
+                     double* min_d2, unsigned long long* key2, const void* filter, void* stream) {
     if (feats == nullptr || centers == nullptr || min_d2 == nullptr || key2 == nullptr) return DAS_ERR_INVALID_ARG;
     if (N <= 0 || D <= 0 || L <= 0 || row_begin < 0 || row_end > N || row_begin >= row_end) return DAS_ERR_INVALID_ARG;
     int rc = ensure_step_table();
     if (rc != DAS_OK) return rc;
     cudaStream_t st = (cudaStream_t)stream;
     const int grid = kc_grid(row_end - row_begin);
-    rc = kc_launch<0>(kc_vec4(feats, D), grid, st, feats, D, row_begin, row_end, centers, L, min_d2, nullptr, 0,
-                      g_step_table, nullptr, 0);
+    if (filter != nullptr)
+        rc = kc_launch_finit(kc_vec4(feats, D), grid, st, feats, D, row_begin, row_end, centers, L, min_d2, g_step_table,
+                             kc_filter_view(filter, N, D, row_end - row_begin));
+    else
+        rc = kc_launch<0>(kc_vec4(feats, D), grid, st, feats, D, row_begin, row_end, centers, L, min_d2, nullptr, 0,
+                          g_step_table, nullptr, 0);
     if (rc != DAS_OK) return rc;
     DAS_LAUNCH(kcenter_key_kernel, 1, 1, 0, st, g_step_table, grid, key2, nullptr, 0);
     DAS_CHECK_LAUNCH();
@@ -200,15 +424,22 @@ int das_kcenter_init(const float* feats, int N, int D, int row_begin, int row_en
 }
 
 int das_kcenter_step(const float* feats, int N, int D, int row_begin, int row_end, const int32_t* centre_idx,
-                     double* min_d2, unsigned long long* key2, void* stream) {
+                     double* min_d2, unsigned long long* key2, const void* filter, void* stream) {
     if (feats == nullptr || centre_idx == nullptr || min_d2 == nullptr || key2 == nullptr) return DAS_ERR_INVALID_ARG;
     if (N <= 0 || D <= 0 || row_begin < 0 || row_end > N || row_begin >= row_end) return DAS_ERR_INVALID_ARG;
     int rc = ensure_step_table();
     if (rc != DAS_OK) return rc;
     cudaStream_t st = (cudaStream_t)stream;
-    const int grid = kc_grid(row_end - row_begin);
-    rc = kc_launch<1>(kc_vec4(feats, D), grid, st, feats, D, row_begin, row_end, centre_idx, 1, min_d2, nullptr, 0,
-                      g_step_table, nullptr, 0);
+    int grid;
+    if (filter != nullptr) {
+        grid = kc_fgrid(row_end - row_begin);
+        rc = kc_launch_fstep<1>(kc_vec4(feats, D), grid, st, feats, D, row_begin, row_end, centre_idx, min_d2, nullptr, 0,
+                                g_step_table, nullptr, 0, kc_filter_view(filter, N, D, row_end - row_begin));
+    } else {
+        grid = kc_grid(row_end - row_begin);
+        rc = kc_launch<1>(kc_vec4(feats, D), grid, st, feats, D, row_begin, row_end, centre_idx, 1, min_d2, nullptr, 0,
+                          g_step_table, nullptr, 0);
+    }
     if (rc != DAS_OK) return rc;
     DAS_LAUNCH(kcenter_key_kernel, 1, 1, 0, st, g_step_table, grid, key2, nullptr, 0);
     DAS_CHECK_LAUNCH();
@@ -222,23 +453,48 @@ int das_kcenter_workspace_bytes(int N, int D, size_t* bytes) {
 }
 
 int das_kcenter_greedy(const float* feats, int N, int D, const int32_t* centers, int L, int K, int32_t* picks,
-                       double* min_d, void* workspace, void* stream) {
+                       double* min_d, void* workspace, const void* filter, void* stream) {
     if (feats == nullptr || centers == nullptr || picks == nullptr || min_d == nullptr || workspace == nullptr)
         return DAS_ERR_INVALID_ARG;
     if (N <= 0 || D <= 0 || L <= 0 || K < 0) return DAS_ERR_INVALID_ARG;
     cudaStream_t st = (cudaStream_t)stream;
     const KcWorkspace w = kc_carve(workspace, N);
     const bool v4 = kc_vec4(feats, D);
-    const int grid = kc_grid(N);
-    int rc = kc_launch<0>(v4, grid, st, feats, D, 0, N, centers, L, w.d2, nullptr, 0, w.best[0], nullptr, 0);
-    if (rc != DAS_OK) return rc;
-    for (int s = 0; s < K; ++s) {
-        rc = kc_launch<2>(v4, grid, st, feats, D, 0, N, nullptr, 0, w.d2, w.best[s & 1], grid, w.best[(s + 1) & 1],
-                          picks, s);
+    int rc;
+    if (filter != nullptr) {
+        const KcFilter f = kc_filter_view(filter, N, D, N);
+        int grid = kc_grid(N);
+        rc = kc_launch_finit(v4, grid, st, feats, D, 0, N, centers, L, w.d2, w.best[0], f);
         if (rc != DAS_OK) return rc;
+        int n_prev = grid;
+        grid = kc_fgrid(N);
+        for (int s = 0; s < K; ++s) {
+            rc = kc_launch_fstep<2>(v4, grid, st, feats, D, 0, N, nullptr, w.d2, w.best[s & 1], n_prev, w.best[(s + 1) & 1],
+                                    picks, s, f);
+            if (rc != DAS_OK) return rc;
+            n_prev = grid;
+        }
+    } else {
+        const int grid = kc_grid(N);
+        rc = kc_launch<0>(v4, grid, st, feats, D, 0, N, centers, L, w.d2, nullptr, 0, w.best[0], nullptr, 0);
+        if (rc != DAS_OK) return rc;
+        for (int s = 0; s < K; ++s) {
+            rc = kc_launch<2>(v4, grid, st, feats, D, 0, N, nullptr, 0, w.d2, w.best[s & 1], grid, w.best[(s + 1) & 1],
+                              picks, s);
+            if (rc != DAS_OK) return rc;
+        }
     }
     DAS_LAUNCH(kcenter_sqrt_kernel, kc_grid(N), kKcThreads, 0, st, w.d2, N, min_d);
     DAS_CHECK_LAUNCH();
+    return DAS_OK;
+}
+
+/* host copy of the filter counters: stats[0] = rows re-evaluated exactly, stats[1] = rows screened */
+int das_kcenter_filter_stats(const void* filter, int N, int D, int rows, unsigned long long* stats2, void* stream) {
+    if (filter == nullptr || stats2 == nullptr || N <= 0 || D <= 0 || rows <= 0 || rows > N) return DAS_ERR_INVALID_ARG;
+    const KcFilter f = kc_filter_view(filter, N, D, rows);
+    DAS_CUDA(cudaMemcpyAsync(stats2, f.stats, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    DAS_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
     return DAS_OK;
 }
 

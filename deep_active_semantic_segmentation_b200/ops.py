@@ -249,7 +249,50 @@ def topk(scores: torch.Tensor, k: int, descending: bool, ids: torch.Tensor | Non
 # core-set
 # ---------------------------------------------------------------------------------------------
 
-def kcenter_greedy(feats: torch.Tensor, centers: Sequence[int] | torch.Tensor, K: int):
+class KCenterFilter:
+    """Tensor-core distance filter for K4 (das_kcenter_filter_build): bf16 tcgen05 Gram distances of the row shard
+    [row_begin,row_end) against every candidate centre.  Purely an accelerator - results are bit-identical
+    with and without it."""
+
+    def __init__(self, feats: torch.Tensor, row_begin: int = 0, row_end: int | None = None):
+        feats = _need_cuda(feats, "feats", torch.float32)
+        self.N, self.D = feats.shape
+        self.row_begin, self.row_end = int(row_begin), self.N if row_end is None else int(row_end)
+        self.rows = self.row_end - self.row_begin
+        lib = _lib.load()
+        nbytes = C.c_size_t()
+        check(lib.das_kcenter_filter_bytes(self.N, self.D, self.rows, C.byref(nbytes)), "das_kcenter_filter_bytes")
+        self.nbytes = nbytes.value
+        raw = torch.empty(self.nbytes + 1024, dtype=torch.uint8, device=feats.device)
+        off = (-raw.data_ptr()) % 1024
+        self.blob = raw[off:off + self.nbytes]
+        check(lib.das_kcenter_filter_build(_ptr(feats), self.N, self.D, self.row_begin, self.row_end, _ptr(self.blob),
+                                           _stream()), "das_kcenter_filter_build")
+
+    @staticmethod
+    def bytes_needed(N: int, D: int, rows: int) -> int:
+        nbytes = C.c_size_t()
+        check(_lib.load().das_kcenter_filter_bytes(N, D, rows, C.byref(nbytes)), "das_kcenter_filter_bytes")
+        return nbytes.value
+
+    def stats(self):
+        """(exact float64 row evaluations, rows screened) so far."""
+        out = (C.c_uint64 * 2)()
+        check(_lib.load().das_kcenter_filter_stats(_ptr(self.blob), self.N, self.D, self.rows, out, _stream()),
+              "das_kcenter_filter_stats")
+        return int(out[0]), int(out[1])
+
+
+def _filter_ptr(flt, feats, row_begin, row_end):
+    if flt is None:
+        return None
+    N, D = feats.shape
+    if (flt.N, flt.D, flt.row_begin, flt.row_end) != (N, D, row_begin, row_end):
+        raise DasError("KCenterFilter was built for a different feature matrix / row shard")
+    return _ptr(flt.blob)
+
+
+def kcenter_greedy(feats: torch.Tensor, centers: Sequence[int] | torch.Tensor, K: int, flt: KCenterFilter | None = None):
     """Single-GPU k-center greedy -> (picks int32 [K], min_dist f64 [N]) on the device."""
     feats = _need_cuda(feats, "feats", torch.float32)
     N, D = feats.shape
@@ -261,17 +304,25 @@ def kcenter_greedy(feats: torch.Tensor, centers: Sequence[int] | torch.Tensor, K
     picks = torch.empty(max(K, 1), dtype=torch.int32, device=feats.device)
     min_d = torch.empty(N, dtype=torch.float64, device=feats.device)
     check(lib.das_kcenter_greedy(_ptr(feats), N, D, _ptr(cen), cen.numel(), K, _ptr(picks), _ptr(min_d), _ptr(ws),
-                                 _stream()), "das_kcenter_greedy")
+                                 _filter_ptr(flt, feats, 0, N), _stream()), "das_kcenter_greedy")
     return picks[:K], min_d
 
 
-def kcenter_init(feats, row_begin, row_end, centers, min_d2, key2):
+def kcenter_init(feats, row_begin, row_end, centers, min_d2, key2, flt: KCenterFilter | None = None):
     N, D = feats.shape
     check(_lib.load().das_kcenter_init(_ptr(feats), N, D, row_begin, row_end, _ptr(centers), centers.numel(),
-                                       _ptr(min_d2), _ptr(key2), _stream()), "das_kcenter_init")
+                                       _ptr(min_d2), _ptr(key2), _filter_ptr(flt, feats, row_begin, row_end), _stream()),
+          "das_kcenter_init")
 
 
-def kcenter_step(feats, row_begin, row_end, centre_idx, min_d2, key2):
+def kcenter_step(feats, row_begin, row_end, centre_idx, min_d2, key2, flt: KCenterFilter | None = None):
     N, D = feats.shape
     check(_lib.load().das_kcenter_step(_ptr(feats), N, D, row_begin, row_end, _ptr(centre_idx), _ptr(min_d2),
-                                       _ptr(key2), _stream()), "das_kcenter_step")
+                                       _ptr(key2), _filter_ptr(flt, feats, row_begin, row_end), _stream()),
+          "das_kcenter_step")
+
+
+def kcenter_filter_budget_ok(N: int, D: int, rows: int, device) -> bool:
+    """Use the tensor-core filter when its N x rows float32 table fits comfortably in free HBM."""
+    free, _total = torch.cuda.mem_get_info(device)
+    return KCenterFilter.bytes_needed(N, D, rows) <= free // 3

@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define DAS_ABI_VERSION 1
+#define DAS_ABI_VERSION 2
 
 typedef enum das_status {
     DAS_OK = 0,
@@ -191,26 +191,43 @@ int das_topk(const float* scores, const int64_t* ids, int n, int k, int descendi
  * fp64 from exact float32 differences.  Rows [row_begin,row_end) are this rank's shard.
  * ------------------------------------------------------------------------------------------ */
 
+/* Tensor-core distance filter (optional, K4 tcgen05 path).
+ * das_kcenter_filter_build makes, for the row shard [row_begin,row_end) of `feats`, a device blob holding
+ *   - a bf16 copy of the features and their exact float64 squared norms,
+ *   - dt[c, i] ~ ||f_i - f_c||^2 for EVERY candidate centre c in [0,N) and every shard row i, computed by one
+ *     bf16 tcgen05 GEMM (TMA-fed, FP32 accumulation in TMEM) fused with the |a|^2 + |b|^2 - 2ab epilogue.
+ * |dt - exact| <= 2^-7 (|f_i|^2 + |f_c|^2) is guaranteed (bf16 rounding + fp32 accumulation, doubled), so
+ * das_kcenter_init / _step / _greedy use dt only to SKIP rows whose float64 minimum provably cannot change
+ * and re-evaluate the others exactly: min_d2 and the picks are bit-identical with and without a filter.
+ * The blob (1024-byte aligned, das_kcenter_filter_bytes) is N*rows*4 bytes + O(N*D): 0.44 GB for N = 10 000.
+ * Pass filter = NULL to the functions below for the plain float64 path (any N). */
+int das_kcenter_filter_bytes(int N, int D, int rows, size_t* bytes);
+int das_kcenter_filter_build(const float* feats, int N, int D, int row_begin, int row_end, void* filter,
+                             void* stream);
+/* HOST out: stats2[0] = exact float64 row evaluations so far, stats2[1] = rows screened (synchronises `stream`) */
+int das_kcenter_filter_stats(const void* filter, int N, int D, int rows, unsigned long long* stats2, void* stream);
+
 /* min_d2[i - row_begin] = min_l ||f_i - f_centers[l]||^2 (fp64) for the L initial centres
- * (core_set.py:19,32-36); also writes the packed argmax key of the shard to *key:
- * (float64 bits of max min_d2 are order preserving since d2 >= 0) key = max over rows of
- * pack(min_d2[i], i) with ties -> lowest i (np.argmax, core_set.py:22). */
+ * (core_set.py:19,32-36); also writes the packed argmax key of the shard to key2:
+ * key2[0] = float64 bits of max min_d2 (order preserving since d2 >= 0), key2[1] = its row index, ties ->
+ * lowest i (np.argmax, core_set.py:22). */
 int das_kcenter_init(const float* feats, int N, int D, int row_begin, int row_end,
                      const int32_t* centers, int L, double* min_d2, unsigned long long* key2,
-                     void* stream);
+                     const void* filter, void* stream);
 
 /* One greedy step: centre = the row index held in *centre_idx (device int32); for every shard row
  * min_d2 = min(min_d2, ||f_i - f_centre||^2) (core_set.py:26,37-38) and the new shard argmax is
  * written to key2[0] (bits of the max), key2[1] (row index). */
 int das_kcenter_step(const float* feats, int N, int D, int row_begin, int row_end,
                      const int32_t* centre_idx, double* min_d2, unsigned long long* key2,
-                     void* stream);
+                     const void* filter, void* stream);
 
 /* Whole single-GPU greedy loop, no host round trip per step: picks int32 [K], min_d f64 [N]
- * (final euclidean min-distances, i.e. sqrt).  workspace: das_kcenter_workspace_bytes(). */
+ * (final euclidean min-distances, i.e. sqrt).  workspace: das_kcenter_workspace_bytes().
+ * filter: blob built with row_begin = 0, row_end = N, or NULL. */
 int das_kcenter_workspace_bytes(int N, int D, size_t* bytes);
 int das_kcenter_greedy(const float* feats, int N, int D, const int32_t* centers, int L, int K,
-                       int32_t* picks, double* min_d, void* workspace, void* stream);
+                       int32_t* picks, double* min_d, void* workspace, const void* filter, void* stream);
 
 #ifdef __cplusplus
 }

@@ -200,3 +200,105 @@ def test_kcenter_odd_dimension_and_baseline_size_properties():
     sub = feats[p + list(range(L))].double()
     d_all = torch.cdist(feats.double(), sub).min(dim=1).values.cpu().numpy()
     np.testing.assert_allclose(md, d_all, rtol=1e-9, atol=1e-5)
+
+
+# ------------------------------------------------------------------ k-center, tensor-core distance filter
+
+def _filter_table(flt):
+    """(dt [N, ld] float32 view, exact float64 squared norms [N]) of a KCenterFilter blob (layout: gram.cuh)."""
+    Dp = -(-flt.D // 64) * 64
+    ld = -(-flt.rows // 32) * 32
+    a = lambda x, al: -(-x // al) * al
+    off_n64 = a(flt.N * Dp * 2, 1024)
+    off_n32 = off_n64 + a(flt.N * 8, 256)
+    off_dt = off_n32 + a(flt.N * 4, 256) + 256
+    dt = flt.blob[off_dt:off_dt + flt.N * ld * 4].view(torch.float32).view(flt.N, ld)
+    n64 = flt.blob[off_n64:off_n64 + flt.N * 8].view(torch.float64)
+    return dt, n64
+
+
+@pytest.mark.parametrize("N,D,lo,hi", [(300, 64, 0, 300), (1000, 200, 0, 1000), (777, 130, 129, 650), (2048, 2048, 0, 2048)])
+def test_gram_filter_distances_respect_the_proven_bound(N, D, lo, hi):
+    """tcgen05 bf16 distances vs exact float64: |dt - d2| <= 2^-7 (|a|^2 + |b|^2) for every (centre, row) pair."""
+    ops = _ops()
+    f = synth.coreset_features(5, N, D)
+    feats = torch.from_numpy(f).cuda()
+    flt = ops.KCenterFilter(feats, lo, hi)
+    dt, n64 = _filter_table(flt)
+    fd = feats.double()
+    exact = torch.cdist(fd, fd[lo:hi]) ** 2                      # [N centres, rows]
+    nrm = (fd * fd).sum(1)
+    np.testing.assert_allclose(n64.cpu().numpy(), nrm.cpu().numpy(), rtol=1e-12)
+    bound = (nrm[:, None] + nrm[None, lo:hi]) / 128.0
+    err = (dt[:, :hi - lo].double() - exact).abs()
+    assert bool((err <= bound).all()), float((err / bound).max())
+    # and the bound is not vacuous: bf16 errors are far below it but above float32 noise
+    assert float((err / bound).max()) < 0.5
+
+
+@pytest.mark.parametrize("N,D,L,K", [(300, 64, 3, 40), (1500, 257, 7, 100), (4096, 512, 50, 200)])
+def test_kcenter_filtered_is_bit_identical_to_exact(N, D, L, K):
+    ops = _ops()
+    feats = torch.from_numpy(synth.coreset_features(7, N, D)).cuda()
+    p0, m0 = ops.kcenter_greedy(feats, list(range(L)), K)
+    flt = ops.KCenterFilter(feats)
+    p1, m1 = ops.kcenter_greedy(feats, list(range(L)), K, flt)
+    assert p0.cpu().tolist() == p1.cpu().tolist()
+    assert torch.equal(m0, m1)                                   # float64 min-distances: bit identical
+    exact, screened = flt.stats()
+    assert screened == K * N and 0 < exact < screened + N * L     # the filter did skip rows
+    want, wm = R.kcenter_greedy(feats.cpu().numpy(), list(range(L)), K)
+    assert p1.cpu().tolist() == want
+
+
+def test_kcenter_filtered_adversarial_duplicates_and_near_ties():
+    """Duplicated rows, rows at distance ~1e-4 of each other and a constant cluster: the filter must flag them
+    all and the float64 result must not change."""
+    ops = _ops()
+    rng = np.random.default_rng(9)
+    base = rng.standard_normal((64, 96)).astype(np.float32)
+    f = np.concatenate([base, base, base + np.float32(1e-4) * rng.standard_normal((64, 96)).astype(np.float32),
+                        np.ones((40, 96), np.float32)]).astype(np.float32)
+    feats = torch.from_numpy(f).cuda()
+    p0, m0 = ops.kcenter_greedy(feats, [0, 1], 60)
+    p1, m1 = ops.kcenter_greedy(feats, [0, 1], 60, ops.KCenterFilter(feats))
+    assert p0.cpu().tolist() == p1.cpu().tolist() and torch.equal(m0, m1)
+
+
+def test_kcenter_sharded_steps_with_filter_match_single_shot():
+    """The step-wise entry points (multi-GPU path) on two row shards of one device, with per-shard filters."""
+    ops = _ops()
+    N, D, L, K = 1200, 160, 5, 50
+    feats = torch.from_numpy(synth.coreset_features(13, N, D)).cuda()
+    want, wm = ops.kcenter_greedy(feats, list(range(L)), K)
+    shards = [(0, 700), (700, N)]
+    flts = [ops.KCenterFilter(feats, lo, hi) for lo, hi in shards]
+    cen = torch.arange(L, dtype=torch.int32, device="cuda")
+    md = [torch.empty(hi - lo, dtype=torch.float64, device="cuda") for lo, hi in shards]
+    keys = [torch.zeros(2, dtype=torch.int64, device="cuda") for _ in shards]
+    for (lo, hi), m, k, fl in zip(shards, md, keys, flts):
+        ops.kcenter_init(feats, lo, hi, cen, m, k, fl)
+    picks = []
+    centre = torch.zeros(1, dtype=torch.int32, device="cuda")
+    for _ in range(K):
+        allk = torch.stack(keys)
+        best = allk[:, 0].max()
+        row = int(torch.where(allk[:, 0] == best, allk[:, 1], torch.full_like(allk[:, 1], 2 ** 62)).min())
+        picks.append(row)
+        centre.fill_(row)
+        for (lo, hi), m, k, fl in zip(shards, md, keys, flts):
+            ops.kcenter_step(feats, lo, hi, centre, m, k, fl)
+    assert picks == want.cpu().tolist()
+    assert torch.equal(torch.cat(md).sqrt(), wm)
+
+
+def test_kcenter_baseline_size_filtered_equals_exact():
+    ops = _ops()
+    N, D, L, K = 10000, 2048, 50, 500
+    feats = torch.from_numpy(synth.coreset_features(11, N, D)).cuda()
+    p0, m0 = ops.kcenter_greedy(feats, list(range(L)), K)
+    flt = ops.KCenterFilter(feats)
+    p1, m1 = ops.kcenter_greedy(feats, list(range(L)), K, flt)
+    assert p0.cpu().tolist() == p1.cpu().tolist() and torch.equal(m0, m1)
+    exact, screened = flt.stats()
+    assert exact < 0.25 * screened
