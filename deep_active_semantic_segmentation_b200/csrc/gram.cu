@@ -26,6 +26,7 @@
 
 #include "das_common.cuh"
 #include "gram.cuh"
+#include "tma_host.cuh"
 
 namespace das {
 
@@ -271,22 +272,27 @@ static EncodeTiledFn encode_tiled_fn() {
     return fn;
 }
 
-// bf16 [rows, Dp] row-major -> boxes of box_rows x 64 elements, 128-byte swizzle, zero fill out of bounds
-static int make_map(CUtensorMap* map, const __nv_bfloat16* base, int rows, int Dp, int box_rows) {
+int make_tensor_map(CUtensorMap* map, CUtensorMapDataType dtype, int rank, const void* base, const cuuint64_t* dims,
+                    const cuuint64_t* strides, const cuuint32_t* box, CUtensorMapSwizzle swizzle) {
     EncodeTiledFn enc = encode_tiled_fn();
     if (enc == nullptr) return DAS_ERR_CUDA;
-    const cuuint64_t dims[2] = {(cuuint64_t)Dp, (cuuint64_t)rows};
-    const cuuint64_t strides[1] = {(cuuint64_t)Dp * sizeof(__nv_bfloat16)};
-    const cuuint32_t box[2] = {(cuuint32_t)kBK, (cuuint32_t)box_rows};
-    const cuuint32_t estr[2] = {1, 1};
-    const CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<__nv_bfloat16*>(base), dims, strides, box,
-                           estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                           CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    const cuuint32_t estr[3] = {1, 1, 1};
+    const CUresult r = enc(map, dtype, (cuuint32_t)rank, const_cast<void*>(base), dims, strides, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
         g_last_cuda_error = (int)r;
         return DAS_ERR_CUDA;
     }
     return DAS_OK;
+}
+
+// bf16 [rows, Dp] row-major -> boxes of box_rows x 64 elements, 128-byte swizzle, zero fill out of bounds
+static int make_map(CUtensorMap* map, const __nv_bfloat16* base, int rows, int Dp, int box_rows) {
+    const cuuint64_t dims[2] = {(cuuint64_t)Dp, (cuuint64_t)rows};
+    const cuuint64_t strides[1] = {(cuuint64_t)Dp * sizeof(__nv_bfloat16)};
+    const cuuint32_t box[2] = {(cuuint32_t)kBK, (cuuint32_t)box_rows};
+    return make_tensor_map(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, base, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
 }
 
 KcFilterLayout kc_filter_layout(int N, int D, int rows) {

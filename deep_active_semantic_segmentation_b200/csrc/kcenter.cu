@@ -37,6 +37,7 @@ __device__ __forceinline__ double warp_dist2(const float* __restrict__ a, const 
     if (VEC4) {
         const float4* a4 = reinterpret_cast<const float4*>(a);
         const float4* b4 = reinterpret_cast<const float4*>(b);
+#pragma unroll 8  // 16 independent 128-bit loads in flight per lane: the loop is L2-latency bound otherwise
         for (int i = lane; i < D / 4; i += 32) {
             const float4 x = a4[i], y = b4[i];
             const double d0 = (double)x.x - (double)y.x, d1 = (double)x.y - (double)y.y;
@@ -225,7 +226,7 @@ __global__ void __launch_bounds__(kKcThreads) kcenter_fstep_kernel(const float* 
                                                                    double* __restrict__ min_d2,
                                                                    const KcBest* __restrict__ prev_best, int n_prev,
                                                                    KcBest* __restrict__ next_best, int32_t* picks, int step,
-                                                                   const KcFilter f) {
+                                                                   const KcFilter f, int stage_centre) {
     __shared__ double sv[kKcWarps];
     __shared__ int si[kKcWarps];
     __shared__ int centre_s;
@@ -235,8 +236,20 @@ __global__ void __launch_bounds__(kKcThreads) kcenter_fstep_kernel(const float* 
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int centre = MODE == 1 ? centres[0] : kc_table_argmax(prev_best, n_prev, sv, si, &centre_s, picks, step);
     const double nc = f.nrm[centre];
-    const float* fc = feats + (size_t)centre * D;
     const float* dtc = f.dt + (size_t)centre * f.ld;
+    // every exact evaluation of this launch is against the same centre row: stage it in shared memory once
+    extern __shared__ float4 centre_row[];
+    const float* fc = feats + (size_t)centre * D;
+    if (stage_centre) {
+        if (VEC4) {
+            const float4* src = reinterpret_cast<const float4*>(fc);
+            for (int i = tid; i < D / 4; i += kKcThreads) centre_row[i] = src[i];
+        } else {
+            float* dst = reinterpret_cast<float*>(centre_row);
+            for (int i = tid; i < D; i += kKcThreads) dst[i] = fc[i];
+        }
+        fc = reinterpret_cast<const float*>(centre_row);  // visible after the first __syncthreads() of the row loop
+    }
 
     double bv = -1.0;
     int bi = -1;
@@ -379,12 +392,15 @@ template <int MODE>
 static int kc_launch_fstep(bool v4, int grid, cudaStream_t st, const float* feats, int D, int rb, int re,
                            const int32_t* centres, double* min_d2, const KcBest* prev, int n_prev, KcBest* next,
                            int32_t* picks, int step, const KcFilter& f) {
+    const size_t row_bytes = (size_t)D * sizeof(float);
+    const int stage_centre = row_bytes <= 40 * 1024 ? 1 : 0;  // fits the default dynamic shared-memory limit
+    const size_t smem = stage_centre ? align_up(row_bytes, 16) : 0;
     if (v4)
-        DAS_LAUNCH((kcenter_fstep_kernel<true, MODE>), grid, kKcThreads, 0, st, feats, D, rb, re, centres, min_d2, prev,
-                   n_prev, next, picks, step, f);
+        DAS_LAUNCH((kcenter_fstep_kernel<true, MODE>), grid, kKcThreads, smem, st, feats, D, rb, re, centres, min_d2, prev,
+                   n_prev, next, picks, step, f, stage_centre);
     else
-        DAS_LAUNCH((kcenter_fstep_kernel<false, MODE>), grid, kKcThreads, 0, st, feats, D, rb, re, centres, min_d2, prev,
-                   n_prev, next, picks, step, f);
+        DAS_LAUNCH((kcenter_fstep_kernel<false, MODE>), grid, kKcThreads, smem, st, feats, D, rb, re, centres, min_d2, prev,
+                   n_prev, next, picks, step, f, stage_centre);
     DAS_CHECK_LAUNCH();
     return DAS_OK;
 }

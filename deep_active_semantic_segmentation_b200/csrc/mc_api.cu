@@ -1,7 +1,10 @@
 // extern "C" entry points of the Monte-Carlo reduction (K1/K2): validation, state layout, dispatch.
 #include <math.h>
 
+#include <stdlib.h>
+
 #include "mc_kernels.cuh"
+#include "tma_host.cuh"
 
 namespace das {
 
@@ -12,7 +15,8 @@ unsigned long long g_launch_count = 0;
 #define DAS_DECL_RANGE(LO, HI)                                                                         \
     int dispatch_accumulate_##LO##_##HI(const McAccParams&, int, int, int, cudaStream_t);             \
     int dispatch_finalize_##LO##_##HI(const McFinParams&, int, int, int, cudaStream_t);               \
-    int dispatch_score_##LO##_##HI(const McScoreParams&, int, int, int, cudaStream_t);
+    int dispatch_score_##LO##_##HI(const McScoreParams&, int, int, int, cudaStream_t);                \
+    int dispatch_score_tma_##LO##_##HI(const McTmaParams&, int, int, cudaStream_t);
 DAS_DECL_RANGE(2, 9)
 DAS_DECL_RANGE(10, 16)
 DAS_DECL_RANGE(17, 20)
@@ -45,6 +49,16 @@ int dispatch_score(const McScoreParams& p, int B, int v4, int f, cudaStream_t st
     if (C <= 24) return dispatch_score_21_24(p, B, v4, f, st);
     if (C <= 28) return dispatch_score_25_28(p, B, v4, f, st);
     return dispatch_score_29_32(p, B, v4, f, st);
+}
+
+int dispatch_score_tma(const McTmaParams& p, int f, int ctas, cudaStream_t st) {
+    const int C = p.fin.C;
+    if (C <= 9) return dispatch_score_tma_2_9(p, f, ctas, st);
+    if (C <= 16) return dispatch_score_tma_10_16(p, f, ctas, st);
+    if (C <= 20) return dispatch_score_tma_17_20(p, f, ctas, st);
+    if (C <= 24) return dispatch_score_tma_21_24(p, f, ctas, st);
+    if (C <= 28) return dispatch_score_tma_25_28(p, f, ctas, st);
+    return dispatch_score_tma_29_32(p, f, ctas, st);
 }
 
 int mc_validate(const das_mc_desc* d) {
@@ -91,7 +105,10 @@ McLayout mc_layout(const das_mc_desc& d) {
     L.votes = off;
     if (keep && (d.flags & DAS_MC_VOTES)) off += align_up((size_t)d.B * d.T_cap * HW, 256);
     L.partials = off;
-    off += align_up((size_t)d.B * L.blocks_fused * DAS_N_SCORES * sizeof(float), 256);
+    // sized for the finest block partition any kernel uses (the TMA kernel: 256-pixel tiles)
+    const int blocks_tma = (int)((HW + kTmaPix - 1) / kTmaPix);
+    const int blocks_max = L.blocks_fused > blocks_tma ? L.blocks_fused : blocks_tma;
+    off += align_up((size_t)d.B * blocks_max * DAS_N_SCORES * sizeof(float), 256);
     L.total = off;
     return L;
 }
@@ -189,6 +206,46 @@ static int reduce_partials(const das_mc_desc* desc, const McFinParams& p, float*
     return DAS_OK;
 }
 
+// ---- TMA-staged single-shot path -------------------------------------------------------------
+static McTmaParams g_tma_params;  // 4.3 KB: kept off the stack; the ABI is thread-compatible, not thread-safe
+
+// DAS_MC_TMA=0 forces the LDG kernel (A/B measurements, tests of both paths); DAS_MC_TMA_CTAS = CTAs per SM
+static bool tma_enabled() {
+    const char* e = getenv("DAS_MC_TMA");
+    return e == nullptr || e[0] != '0';
+}
+static int tma_ctas_per_sm() {
+    const char* e = getenv("DAS_MC_TMA_CTAS");
+    const int v = e != nullptr ? atoi(e) : 3;
+    return v >= 1 && v <= 8 ? v : 3;
+}
+static bool tma_eligible(const das_mc_desc* desc, const McScoreParams& q) {
+    if (!tma_enabled() || q.acc.pass_begin != 0) return false;
+    const long long HW = (long long)desc->H * desc->W;
+    if (HW % 4 != 0 || HW < kTmaPix) return false;  // plane strides must be multiples of 16 bytes
+    for (int g = 0; g < q.acc.n_passes; ++g)
+        if (!aligned16(q.acc.logits[g])) return false;
+    return true;
+}
+static int fill_tma_params(const das_mc_desc* desc, const McScoreParams& q, McTmaParams* out) {
+    const unsigned long long HW = (unsigned long long)desc->H * desc->W;
+    const cuuint64_t dims[3] = {HW, (cuuint64_t)desc->C, (cuuint64_t)desc->B};
+    const cuuint64_t strides[2] = {HW * sizeof(float), HW * desc->C * sizeof(float)};
+    const cuuint32_t box[3] = {(cuuint32_t)kTmaPix, (cuuint32_t)desc->C, 1};
+    for (int g = 0; g < q.acc.n_passes; ++g) {
+        const int rc = make_tensor_map(&out->maps[g], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, q.acc.logits[g], dims, strides,
+                                       box, CU_TENSOR_MAP_SWIZZLE_NONE);
+        if (rc != DAS_OK) return rc;
+    }
+    out->fin = q.fin;
+    out->HW = (long long)HW;
+    out->B = desc->B;
+    out->n_passes = q.acc.n_passes;
+    out->tiles_per_image = q.fin.blocks_per_image;  // 256-pixel blocks, same partials layout as the VEC=2 LDG kernel
+    out->stages = 0;
+    return DAS_OK;
+}
+
 extern "C" {
 
 const char* das_strerror(int status) {
@@ -263,7 +320,16 @@ int das_mc_accumulate_finalize(const das_mc_desc* desc, void* state, const float
                          margin, weak_labels, mc_layout(*desc).blocks_fused, &q.fin);
     if (rc != DAS_OK) return rc;
     cudaStream_t st = (cudaStream_t)stream;
-    rc = dispatch_score(q, desc->B, acc_vec(*desc), desc->flags & (DAS_MC_VOTES | DAS_MC_PROBS), st);
+    const int flags = desc->flags & (DAS_MC_VOTES | DAS_MC_PROBS);
+    if (tma_eligible(desc, q)) {
+        // whole Monte-Carlo stack in one launch and 16-byte aligned planes: TMA-staged persistent kernel
+        q.fin.blocks_per_image = (int)(((long long)desc->H * desc->W + kTmaPix - 1) / kTmaPix);
+        rc = fill_tma_params(desc, q, &g_tma_params);
+        if (rc != DAS_OK) return rc;
+        rc = dispatch_score_tma(g_tma_params, flags, tma_ctas_per_sm(), st);
+    } else {
+        rc = dispatch_score(q, desc->B, acc_vec(*desc), flags, st);
+    }
     if (rc != DAS_OK) return rc;
     return reduce_partials(desc, q.fin, image_scores, st);
 }

@@ -118,7 +118,43 @@ int launch_score(const McScoreParams& p, int B, int vec, int flags, cudaStream_t
 }
 
 template <int C>
+int launch_score_tma(const McTmaParams& p, int flags, int ctas_per_sm, cudaStream_t st) {
+    const bool probs = flags & DAS_MC_PROBS, votes = flags & DAS_MC_VOTES;
+    // ring depth from the shared memory left per CTA: 227 KB per SM, 1 KB reserved per CTA, ~C/4 + 2 KB static
+    const size_t stage = (size_t)C * kTmaPix * sizeof(float);
+    int stages = 0;
+    for (; ctas_per_sm >= 1; --ctas_per_sm) {
+        const size_t per_cta = (size_t)227 * 1024 / ctas_per_sm - 1024 - ((size_t)C * 256 + 2048);
+        stages = (int)(per_cta / stage);
+        if (stages > kTmaMaxStages) stages = kTmaMaxStages;
+        if (stages >= 2) break;
+    }
+    if (stages < 2) return DAS_ERR_UNSUPPORTED;
+    McTmaParams q = p;
+    q.stages = stages;
+    const size_t smem = stage * stages;
+    const int tiles = p.B * p.tiles_per_image;
+    const int grid = tiles < kNumSMs * ctas_per_sm ? tiles : kNumSMs * ctas_per_sm;
+#define DAS_TMA(P, Q)                                                                              \
+    do {                                                                                           \
+        int rc__ = set_smem(mc_score_tma_kernel<C, P, Q>, smem);                                   \
+        if (rc__ != DAS_OK) return rc__;                                                           \
+        DAS_LAUNCH((mc_score_tma_kernel<C, P, Q>), grid, kTmaThreads, smem, st, q);                \
+    } while (0)
+    if (probs && votes) DAS_TMA(true, true);
+    else if (probs) DAS_TMA(true, false);
+    else DAS_TMA(false, true);
+#undef DAS_TMA
+    DAS_CHECK_LAUNCH();
+    return DAS_OK;
+}
+
+template <int C>
 struct Range {
+    static int score_tma(const McTmaParams& p, int f, int ctas, cudaStream_t st) {
+        if (p.fin.C == C) return launch_score_tma<C>(p, f, ctas, st);
+        return Range<C + 1>::score_tma(p, f, ctas, st);
+    }
     static int score(const McScoreParams& p, int B, int v4, int f, cudaStream_t st) {
         if (p.acc.C == C) return launch_score<C>(p, B, v4, f, st);
         return Range<C + 1>::score(p, B, v4, f, st);
@@ -137,6 +173,7 @@ struct Range<DAS_C_HI + 1> {
     static int acc(const McAccParams&, int, int, int, cudaStream_t) { return DAS_ERR_UNSUPPORTED; }
     static int fin(const McFinParams&, int, int, int, cudaStream_t) { return DAS_ERR_UNSUPPORTED; }
     static int score(const McScoreParams&, int, int, int, cudaStream_t) { return DAS_ERR_UNSUPPORTED; }
+    static int score_tma(const McTmaParams&, int, int, cudaStream_t) { return DAS_ERR_UNSUPPORTED; }
 };
 
 #define DAS_CAT_(a, b, c) a##b##_##c
@@ -150,6 +187,9 @@ int DAS_CAT(dispatch_finalize_, DAS_C_LO, DAS_C_HI)(const McFinParams& p, int B,
 
 int DAS_CAT(dispatch_score_, DAS_C_LO, DAS_C_HI)(const McScoreParams& p, int B, int v4, int f, cudaStream_t st) {
     return Range<DAS_C_LO>::score(p, B, v4, f, st);
+}
+int DAS_CAT(dispatch_score_tma_, DAS_C_LO, DAS_C_HI)(const McTmaParams& p, int f, int ctas, cudaStream_t st) {
+    return Range<DAS_C_LO>::score_tma(p, f, ctas, st);
 }
 
 }  // namespace das

@@ -149,14 +149,23 @@ constexpr size_t acc_smem_bytes(int C, int VEC) { return (size_t)C * kAccThreads
 //     (log-sum-exp form of ceal.py:118: one log2 per pixel instead of one per logit; it differs from
 //      the reference's "+1e-12" form by < 2e-12 per class and has no cancellation, both terms >= 0)
 template <int C, int VEC, bool PROBS, bool VOTES, bool SMEM>
+__device__ __forceinline__ uint32_t mc_pass_math(float (&x)[C][VEC], Acc<C, VEC, SMEM>& acc, float* ent);
+
+template <int C, int VEC, bool PROBS, bool VOTES, bool SMEM>
 __device__ __forceinline__ uint32_t mc_pass(const float* __restrict__ xp, uint32_t plane_bytes,
                                             Acc<C, VEC, SMEM>& acc, float* ent) {
     float x[C][VEC];
-    // plane c of this image lives plane_bytes*c further on: one IMAD.WIDE per address
+    // plane c of this image lives plane_bytes*c further on
     const char* xb = reinterpret_cast<const char*>(xp);
 #pragma unroll
     for (int c = 0; c < C; ++c)
         unpack<VEC>(ldg_stream_v<VEC>(reinterpret_cast<const float*>(xb + (size_t)((uint32_t)c * plane_bytes))), x[c]);
+    return mc_pass_math<C, VEC, PROBS, VOTES, SMEM>(x, acc, ent);
+}
+
+// the arithmetic of one pass on the C x VEC logits already in registers (shared by the LDG and the TMA kernels)
+template <int C, int VEC, bool PROBS, bool VOTES, bool SMEM>
+__device__ __forceinline__ uint32_t mc_pass_math(float (&x)[C][VEC], Acc<C, VEC, SMEM>& acc, float* ent) {
     uint32_t vote_word = 0;
     float inv[VEC];
     float m[VEC];
@@ -398,8 +407,18 @@ __device__ __forceinline__ void store_weak_labels(uint8_t* weak_labels, size_t m
 }
 
 // image pooling: thread -> warp shuffle -> shared memory -> one partial row per block (fixed order)
-template <int VEC, int NT>
-__device__ __forceinline__ void block_partials(float (*sc)[VEC], float (*red)[NT / 32], float* partials_row, int tid) {
+struct SyncBlock {
+    __device__ __forceinline__ void operator()() const { __syncthreads(); }
+};
+// barrier among the first N threads of the block only (named barrier 1): the TMA kernel's consumer warps
+template <int N>
+struct SyncNamed {
+    __device__ __forceinline__ void operator()() const { asm volatile("bar.sync 1, %0;" ::"n"(N) : "memory"); }
+};
+
+template <int VEC, int NT, typename Sync = SyncBlock>
+__device__ __forceinline__ void block_partials(float (*sc)[VEC], float (*red)[NT / 32], float* partials_row, int tid,
+                                               Sync sync = Sync()) {
     const int lane = tid & 31, wid = tid >> 5;
 #pragma unroll
     for (int k = 0; k < DAS_N_SCORES; ++k) {
@@ -409,7 +428,7 @@ __device__ __forceinline__ void block_partials(float (*sc)[VEC], float (*red)[NT
         s = warp_sum(s);
         if (lane == 0) red[k][wid] = s;
     }
-    __syncthreads();
+    sync();
     if (tid < DAS_N_SCORES) {
         float s = 0.f;
 #pragma unroll
@@ -554,6 +573,10 @@ __global__ void __launch_bounds__(kAccThreads, MINB) mc_score_kernel(const McSco
     block_partials<VEC, NT>(sc, red, f.partials + ((size_t)b * f.blocks_per_image + blockIdx.x) * DAS_N_SCORES, tid);
 }
 
+}  // namespace das
+#include "mc_tma.cuh"
+namespace das {
+
 // per-class-count launchers (instantiated in mc_inst.cu for a range of C)
 template <int C>
 int launch_accumulate(const McAccParams& p, int B, int vec, int flags, cudaStream_t st);
@@ -561,9 +584,12 @@ template <int C>
 int launch_finalize(const McFinParams& p, int B, int vec, int flags, cudaStream_t st);
 template <int C>
 int launch_score(const McScoreParams& p, int B, int vec, int flags, cudaStream_t st);
+template <int C>
+int launch_score_tma(const McTmaParams& p, int flags, int ctas_per_sm, cudaStream_t st);
 
 int dispatch_accumulate(const McAccParams& p, int B, int vec, int flags, cudaStream_t st);
 int dispatch_finalize(const McFinParams& p, int B, int vec, int flags, cudaStream_t st);
 int dispatch_score(const McScoreParams& p, int B, int vec, int flags, cudaStream_t st);
+int dispatch_score_tma(const McTmaParams& p, int flags, int ctas_per_sm, cudaStream_t st);
 
 }  // namespace das

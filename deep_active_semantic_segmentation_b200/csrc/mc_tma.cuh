@@ -1,0 +1,169 @@
+// Fused K1+K2 with TMA staging: the single-shot Monte-Carlo reduction (all T passes of a batch in one launch)
+// for planes whose size is a multiple of 4 pixels (Cityscapes-shaped pools).
+//
+// Why: the LDG kernel (mc_score_kernel) is memory-LATENCY bound - a warp issues the 19 loads of a pass, waits,
+// computes, issues the next 19 (profiles/r1_k1_notes.md: long_scoreboard 3.3 of 6.1 stalled warps per issue), and
+// every load pays a 64-bit address add (54 IADD3 per pass).  Here one elected producer thread streams
+// [C x 256 pixel] boxes (one cp.async.bulk.tensor per pass and tile, 19 KB) through a shared-memory ring, so
+// bytes in flight no longer depend on occupancy or on the compute phase, and the consumers read their two
+// pixels of every class with immediate-offset LDS.64 (no address arithmetic).  CTAs are persistent: the ring
+// keeps prefetching the next tile's passes while the consumers finalize the current tile.
+//
+// Same per-pixel arithmetic (mc_pass_math, probs_scores, the byte histogram) and the same 256-pixel block
+// partials as mc_score_kernel<VEC=2>: results are bit-identical between the two kernels.
+#pragma once
+
+#include <cuda.h>
+
+namespace das {
+
+constexpr int kTmaPix = 256;      // pixels per tile: 128 consumer threads x 2 pixels
+constexpr int kTmaThreads = 160;  // 4 consumer warps + 1 producer warp
+constexpr int kTmaMaxStages = 8;
+
+struct McTmaParams {
+    CUtensorMap maps[DAS_MAX_PASS_GROUP];  // one 3-D map (HW, C, B) per pass buffer, box (256, C, 1)
+    McFinParams fin;
+    long long HW;
+    int B, n_passes, tiles_per_image, stages;
+};
+
+__device__ __forceinline__ uint32_t tma_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void tma_mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra WAIT_DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "WAIT_DONE:\n\t"
+        "}\n" ::"r"(bar),
+        "r"(parity)
+        : "memory");
+}
+
+template <int C, bool PROBS, bool VOTES>
+__global__ void __launch_bounds__(kTmaThreads, 3) mc_score_tma_kernel(const __grid_constant__ McTmaParams q) {
+    constexpr int NT = 128, VEC = 2;
+    constexpr uint32_t kStageBytes = (uint32_t)C * kTmaPix * sizeof(float);
+    extern __shared__ __align__(1024) uint8_t ring[];
+    __shared__ uint64_t bars[2 * kTmaMaxStages];
+    __shared__ uint32_t hist32[VOTES ? C * NT * VEC / 4 + 1 : 1];
+    __shared__ float lut[VOTES ? 256 : 1];
+    __shared__ float red[DAS_N_SCORES][NT / 32];
+    uint8_t* hist8 = reinterpret_cast<uint8_t*>(hist32);
+
+    const McFinParams& f = q.fin;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int S = q.stages, T = q.n_passes;
+    const uint32_t ring0 = tma_smem_u32(ring), bar0 = tma_smem_u32(bars);
+    const int total_tiles = q.B * q.tiles_per_image;
+
+    if (tid == 0) {
+        for (int s = 0; s < S; ++s) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar0 + 8u * s), "r"(1) : "memory");       // full
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar0 + 8u * (S + s)), "r"(4) : "memory");  // empty
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    if (warp == 4) {
+        // ===== producer: one thread, one bulk tensor copy per (tile, pass) =====
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                const int b = tile / q.tiles_per_image, px0 = (tile % q.tiles_per_image) * kTmaPix;
+                for (int g = 0; g < T; ++g) {
+                    tma_mbar_wait(bar0 + 8u * (S + stage), phase ^ 1u);
+                    const uint32_t full = bar0 + 8u * stage;
+                    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(full), "r"(kStageBytes)
+                                 : "memory");
+                    asm volatile(
+                        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], "
+                        "[%2];" ::"r"(ring0 + stage * kStageBytes),
+                        "l"(&q.maps[g]), "r"(full), "r"(px0), "r"(0), "r"(b)
+                        : "memory");
+                    if (++stage == S) stage = 0, phase ^= 1u;
+                }
+            }
+        }
+        return;
+    }
+
+    // ===== consumers: 128 threads, 2 pixels each =====
+    const SyncNamed<NT> sync;
+    if (VOTES) {
+        const float Tf = (float)f.T;
+        for (int n = tid; n <= f.T; n += NT) {
+            const float pr = (float)n / Tf;
+            lut[n] = pr * log2f(pr + kEps);  // p * log2(p + 1e-12), p = n / T in float32 (mc_dropout.py:47-48)
+        }
+        sync();
+    }
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int b = tile / q.tiles_per_image, blk = tile % q.tiles_per_image;
+        const long long pix = (long long)blk * kTmaPix + tid * VEC;
+        const bool active = pix < q.HW;
+        if (VOTES) {
+#pragma unroll
+            for (int c = 0; c < C; ++c) store_bytes<VEC>(hist8 + (size_t)(c * NT + tid) * VEC, 0u);  // thread-private
+        }
+        Acc<C, VEC, false> acc;
+        acc.s = nullptr;
+        float ent[VEC], z[VEC];
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) z[j] = 0.f, ent[j] = 0.f;
+#pragma unroll
+        for (int c = 0; c < C; ++c) acc.set(c, z);
+        uint32_t first_vote = 0;
+
+        for (int g = 0; g < T; ++g) {
+            tma_mbar_wait(bar0 + 8u * stage, phase);
+            const float2* sp = reinterpret_cast<const float2*>(ring + stage * kStageBytes) + tid;
+            float x[C][VEC];
+#pragma unroll
+            for (int c = 0; c < C; ++c) {
+                const float2 v = sp[c * (kTmaPix / 2)];
+                x[c][0] = v.x, x[c][1] = v.y;
+            }
+            __syncwarp();
+            if (lane == 0)  // this warp has its copy of the stage in registers: hand the slot back
+                asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar0 + 8u * (S + stage)) : "memory");
+            if (++stage == S) stage = 0, phase ^= 1u;
+            const uint32_t vote_word = mc_pass_math<C, VEC, PROBS, VOTES, false>(x, acc, ent);
+            if (VOTES) {
+                hist_add<VEC, NT>(hist8, vote_word, tid);
+                if (g == 0) first_vote = vote_word;
+            }
+        }
+
+        float sc[DAS_N_SCORES][VEC];
+#pragma unroll
+        for (int k = 0; k < DAS_N_SCORES; ++k)
+#pragma unroll
+            for (int j = 0; j < VEC; ++j) sc[k][j] = 0.f;
+        if (active) {
+            const size_t map_off = (size_t)b * q.HW + pix;
+            bool valid[VEC];
+            load_valid<C, VEC>(f.labels, map_off, valid);
+            if (PROBS) probs_scores<C, VEC>([&](int c, float* a) { acc.get(c, a); }, ent, (float)f.T, valid, sc);
+            if (VOTES) {
+                float ve[VEC];
+                hist_vote_entropy<C, VEC, NT>(hist8, lut, tid, ve);
+#pragma unroll
+                for (int j = 0; j < VEC; ++j) sc[DAS_SCORE_VOTE_ENTROPY][j] = valid[j] ? ve[j] : 0.f;
+                if (f.weak_labels) store_weak_labels<VEC>(f.weak_labels, map_off, first_vote, valid);
+            }
+            store_maps<VEC>(f, map_off, sc, PROBS, VOTES);
+        }
+        block_partials<VEC, NT>(sc, red, f.partials + ((size_t)b * f.blocks_per_image + blk) * DAS_N_SCORES, tid, sync);
+        sync();  // `red` is reused by the next tile
+    }
+}
+
+}  // namespace das
