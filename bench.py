@@ -227,11 +227,14 @@ def run_b200(args):
     if os.path.exists(tf):
         try:
             tj = json.load(open(tf))
-            if tj.get("batch") == B and tj.get("pass_group") == G:
+            if tj.get("batch") == B and tj.get("pass_group") == G and tj.get("tma", False) == tma and tj.get("mode", "full") == args.mode:
                 traffic = tj.get("dram_bytes_per_launch")
         except Exception:
             traffic = None
-    kname = "mc_score_kernel<C=19,VEC=2> (fused K1+K2)" if G >= T else "mc_accumulate_kernel / mc_score_kernel <C=19,VEC=2>"
+    tma = G >= T and os.environ.get("DAS_MC_TMA", "1")[:1] != "0"
+    kname = ("mc_score_tma_kernel<C=19> (fused K1+K2, TMA ring, persistent)" if tma else
+             "mc_score_kernel<C=19,VEC=2> (fused K1+K2, LDG)" if G >= T else
+             "mc_accumulate_kernel / mc_score_kernel <C=19,VEC=2>")
     roofline = {"bound": "hbm", "kernel": kname, "achieved": round(achieved, 1),
                 "peak": peaks["hbm_gbs"], "peak_kind": peak_kind + " copy bandwidth (burst)", "unit": "GB/s",
                 "frac": round(achieved / peaks["hbm_gbs"], 4), "traffic": traffic,

@@ -11,6 +11,7 @@
 // its bf16 distance first and re-evaluate in float64 only the rows whose minimum can change; the values
 // written to min_d2 and the picks are bit-identical to the unfiltered path.
 #include <math.h>
+#include <stdlib.h>
 
 #include "das_common.cuh"
 #include "gram.cuh"
@@ -309,6 +310,171 @@ __global__ void __launch_bounds__(kKcThreads) kcenter_fstep_kernel(const float* 
     }
 }
 
+
+// ---- whole greedy loop in ONE thread-block cluster (single-GPU path with a filter) -----------------
+// 500 dependent steps of a few microseconds each are launch-latency bound as a chain of kernels (~9 us per
+// step measured).  Here 8 CTAs x 1024 threads of one cluster keep min_d2 and the row norms in REGISTERS
+// (up to kClRows rows per thread), stage the centre row in shared memory, exchange each CTA's arg-max
+// through distributed shared memory (st.shared::cluster) and meet at one hardware cluster barrier per
+// step: no kernel boundary, no global-memory round trip for the arg-max.
+constexpr int kClCtas = 8;
+constexpr int kClThreads = 1024;
+constexpr int kClWarps = kClThreads / 32;
+constexpr int kClRows = 4;  // rows per thread -> N <= 8 * 1024 * 4 = 32768
+
+struct __align__(16) ClBest {  // 32 bytes: the (v, nrm) pair is published with one 16-byte remote store
+    double v, nrm;
+    int idx, pad[3];
+};
+
+__device__ __forceinline__ void cluster_barrier() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+template <bool VEC4>
+__global__ void __cluster_dims__(kClCtas, 1, 1) __launch_bounds__(kClThreads, 1)
+    kcenter_cluster_kernel(const float* __restrict__ feats, int N, int D, double* __restrict__ min_d2, int K,
+                           int32_t* __restrict__ picks, double* __restrict__ min_d_out, const KcFilter f, int stage_centre) {
+    extern __shared__ float4 cl_dyn[];  // [centre row][wl_val f64 x 4096][wl_row i32 x 4096]
+    __shared__ ClBest slots[2][kClCtas];
+    __shared__ double sv[kClWarps];
+    __shared__ double sn[kClWarps];
+    __shared__ int si[kClWarps];
+    __shared__ int wl_n;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    uint32_t rank;
+    asm("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
+    const size_t row_f4 = stage_centre ? ((size_t)D * sizeof(float) + 15) / 16 : 0;
+    float* centre_row = reinterpret_cast<float*>(cl_dyn);
+    double* wl_val = reinterpret_cast<double*>(cl_dyn + row_f4);
+    int* wl_row = reinterpret_cast<int*>(wl_val + kClThreads * kClRows);
+
+    // rows of this thread: g + j * 8192 (coalesced across the cluster for every j)
+    const int g = (int)rank * kClThreads + tid;
+    double m[kClRows], nr[kClRows];
+#pragma unroll
+    for (int j = 0; j < kClRows; ++j) {
+        const int row = g + j * kClCtas * kClThreads;
+        m[j] = row < N ? min_d2[row] : -1.0;
+        nr[j] = row < N ? f.nrm[row] : 0.0;
+    }
+    unsigned long long n_exact = 0;
+    int parity = 0;
+    cluster_barrier();  // every CTA of the cluster is resident before the first remote store
+
+    for (int s = 0; s < K; ++s) {
+        // ---- local arg-max of the current min_d2 ----
+        double bv = -1.0, bn = 0.0;
+        int bi = -1;
+#pragma unroll
+        for (int j = 0; j < kClRows; ++j) {
+            const int row = g + j * kClCtas * kClThreads;
+            if (row < N && (bi < 0 || kc_better(m[j], row, bv, bi))) bv = m[j], bi = row, bn = nr[j];
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const double ov = __shfl_xor_sync(0xffffffffu, bv, o), on = __shfl_xor_sync(0xffffffffu, bn, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            if (oi >= 0 && (bi < 0 || kc_better(ov, oi, bv, bi))) bv = ov, bi = oi, bn = on;
+        }
+        if (lane == 0) sv[wid] = bv, si[wid] = bi, sn[wid] = bn;
+        __syncthreads();
+        if (wid == 0) {
+            bv = sv[lane], bi = si[lane], bn = sn[lane];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const double ov = __shfl_xor_sync(0xffffffffu, bv, o), on = __shfl_xor_sync(0xffffffffu, bn, o);
+                const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+                if (oi >= 0 && (bi < 0 || kc_better(ov, oi, bv, bi))) bv = ov, bi = oi, bn = on;
+            }
+            if (lane < kClCtas) {  // lane t publishes this CTA's best in CTA t's slot table
+                const uint32_t local = (uint32_t)__cvta_generic_to_shared(&slots[parity][rank]);
+                uint32_t remote;
+                asm("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local), "r"(lane));
+                asm volatile("st.shared::cluster.v2.f64 [%0], {%1, %2};" ::"r"(remote), "d"(bv), "d"(bn) : "memory");
+                asm volatile("st.shared::cluster.u32 [%0], %1;" ::"r"(remote + 16), "r"(bi) : "memory");
+            }
+        }
+        cluster_barrier();
+        // ---- every thread reduces the 8 published records: the next centre ----
+        double cv = -1.0, nc = 0.0;
+        int centre = -1;
+#pragma unroll
+        for (int r = 0; r < kClCtas; ++r) {
+            const ClBest q = slots[parity][r];
+            if (q.idx >= 0 && (centre < 0 || kc_better(q.v, q.idx, cv, centre))) cv = q.v, centre = q.idx, nc = q.nrm;
+        }
+        parity ^= 1;
+        if (rank == 0 && tid == 0) picks[s] = centre;
+
+        // ---- screen own rows with the tensor-core distances, exact float64 for the rest ----
+        // (the screening distances are requested first so that their HBM latency overlaps the centre-row copy)
+        const float* dtc = f.dt + (size_t)centre * f.ld;
+        float dtv[kClRows];
+#pragma unroll
+        for (int j = 0; j < kClRows; ++j) {
+            const int row = g + j * kClCtas * kClThreads;
+            dtv[j] = row < N ? dtc[row] : 0.f;
+        }
+        const float* fc = feats + (size_t)centre * D;
+        if (stage_centre) {
+            if (VEC4) {
+                const float4* src = reinterpret_cast<const float4*>(fc);
+                for (int i = tid; i < D / 4; i += kClThreads) cl_dyn[i] = src[i];
+            } else {
+                for (int i = tid; i < D; i += kClThreads) centre_row[i] = fc[i];
+            }
+            fc = centre_row;
+        }
+        if (tid == 0) wl_n = 0;
+        __syncthreads();
+        int slot[kClRows];
+#pragma unroll
+        for (int j = 0; j < kClRows; ++j) {
+            const int row = g + j * kClCtas * kClThreads;
+            bool need = false;
+            if (row < N) need = (double)dtv[j] - kFilterDelta * (nr[j] + nc) <= m[j];
+            slot[j] = -1;
+            const unsigned mask = __ballot_sync(0xffffffffu, need);
+            if (mask) {
+                int wbase = 0;
+                if (lane == 0) wbase = atomicAdd(&wl_n, __popc(mask));
+                wbase = __shfl_sync(0xffffffffu, wbase, 0);
+                if (need) {
+                    slot[j] = wbase + __popc(mask & ((1u << lane) - 1u));
+                    wl_row[slot[j]] = row;
+                }
+            }
+        }
+        __syncthreads();
+        const int n_work = wl_n;
+        for (int k = wid; k < n_work; k += kClWarps) {
+            const double d = warp_dist2<VEC4>(feats + (size_t)wl_row[k] * D, fc, D, lane);
+            if (lane == 0) wl_val[k] = d;
+        }
+        if (tid == 0) n_exact += (unsigned long long)n_work;
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < kClRows; ++j)
+            if (slot[j] >= 0) m[j] = fmin(m[j], wl_val[slot[j]]);
+    }
+
+#pragma unroll
+    for (int j = 0; j < kClRows; ++j) {
+        const int row = g + j * kClCtas * kClThreads;
+        if (row < N) {
+            min_d2[row] = m[j];
+            min_d_out[row] = sqrt(m[j]);
+        }
+    }
+    if (tid == 0) {
+        if (n_exact) atomicAdd(f.stats, n_exact);
+        if (rank == 0) atomicAdd(f.stats + 1, (unsigned long long)N * K);
+    }
+    cluster_barrier();  // no CTA leaves while a peer could still address its shared memory
+}
+
 // reduce a block table to the packed pair key2 = {fp64 bits of the max, row index}
 __global__ void kcenter_key_kernel(const KcBest* best, int n, unsigned long long* key2, int32_t* picks, int step) {
     double bv = -1.0;
@@ -409,6 +575,12 @@ static int kc_launch_fstep(bool v4, int grid, cudaStream_t st, const float* feat
 
 using namespace das;
 
+// DAS_KC_CLUSTER=0 forces the chain-of-launches greedy loop (A/B measurements, tests of both paths)
+static bool kc_cluster_enabled() {
+    const char* e = getenv("DAS_KC_CLUSTER");
+    return e == nullptr || e[0] != '0';
+}
+
 // scratch table for the step-wise (multi-GPU) entry points: one per process is enough because the
 // ABI is thread-compatible, not thread-safe.
 static KcBest* g_step_table = nullptr;
@@ -482,6 +654,23 @@ int das_kcenter_greedy(const float* feats, int N, int D, const int32_t* centers,
         int grid = kc_grid(N);
         rc = kc_launch_finit(v4, grid, st, feats, D, 0, N, centers, L, w.d2, w.best[0], f);
         if (rc != DAS_OK) return rc;
+        if (N <= kClCtas * kClThreads * kClRows && kc_cluster_enabled()) {
+            // the whole loop inside one thread-block cluster
+            const size_t row_bytes = (size_t)D * sizeof(float);
+            const int stage_centre = row_bytes <= 96 * 1024 ? 1 : 0;
+            const size_t smem = (stage_centre ? align_up(row_bytes, 16) : 0) + (size_t)kClThreads * kClRows * (8 + 4);
+            if (v4) {
+                DAS_CUDA(cudaFuncSetAttribute(kcenter_cluster_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                DAS_LAUNCH((kcenter_cluster_kernel<true>), kClCtas, kClThreads, smem, st, feats, N, D, w.d2, K, picks, min_d, f,
+                           stage_centre);
+            } else {
+                DAS_CUDA(cudaFuncSetAttribute(kcenter_cluster_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                DAS_LAUNCH((kcenter_cluster_kernel<false>), kClCtas, kClThreads, smem, st, feats, N, D, w.d2, K, picks, min_d, f,
+                           stage_centre);
+            }
+            DAS_CHECK_LAUNCH();
+            return DAS_OK;
+        }
         int n_prev = grid;
         grid = kc_fgrid(N);
         for (int s = 0; s < K; ++s) {

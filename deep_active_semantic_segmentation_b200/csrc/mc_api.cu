@@ -216,8 +216,8 @@ static bool tma_enabled() {
 }
 static int tma_ctas_per_sm() {
     const char* e = getenv("DAS_MC_TMA_CTAS");
-    const int v = e != nullptr ? atoi(e) : 3;
-    return v >= 1 && v <= 8 ? v : 3;
+    const int v = e != nullptr ? atoi(e) : 0;  // 0 = per class count (mc_tma.cuh)
+    return v >= 1 && v <= 8 ? v : 0;
 }
 static bool tma_eligible(const das_mc_desc* desc, const McScoreParams& q) {
     if (!tma_enabled() || q.acc.pass_begin != 0) return false;

@@ -123,6 +123,7 @@ int launch_score_tma(const McTmaParams& p, int flags, int ctas_per_sm, cudaStrea
     // ring depth from the shared memory left per CTA: 227 KB per SM, 1 KB reserved per CTA, ~C/4 + 2 KB static
     const size_t stage = (size_t)C * kTmaPix * sizeof(float);
     int stages = 0;
+    if (ctas_per_sm <= 0) ctas_per_sm = tma_ctas_per_sm(C);
     for (; ctas_per_sm >= 1; --ctas_per_sm) {
         const size_t per_cta = (size_t)227 * 1024 / ctas_per_sm - 1024 - ((size_t)C * 256 + 2048);
         stages = (int)(per_cta / stage);
@@ -134,12 +135,19 @@ int launch_score_tma(const McTmaParams& p, int flags, int ctas_per_sm, cudaStrea
     q.stages = stages;
     const size_t smem = stage * stages;
     const int tiles = p.B * p.tiles_per_image;
-    const int grid = tiles < kNumSMs * ctas_per_sm ? tiles : kNumSMs * ctas_per_sm;
+    // persistent grid = what is actually co-resident (registers can allow fewer CTAs than shared memory does)
 #define DAS_TMA(P, Q)                                                                              \
     do {                                                                                           \
         int rc__ = set_smem(mc_score_tma_kernel<C, P, Q>, smem);                                   \
         if (rc__ != DAS_OK) return rc__;                                                           \
-        DAS_LAUNCH((mc_score_tma_kernel<C, P, Q>), grid, kTmaThreads, smem, st, q);                \
+        int occ__ = 0;                                                                             \
+        cudaError_t e__ = cudaOccupancyMaxActiveBlocksPerMultiprocessor(                           \
+            &occ__, mc_score_tma_kernel<C, P, Q>, kTmaThreads, smem);                              \
+        if (e__ != cudaSuccess) return cuda_fail(e__);                                             \
+        if (occ__ < 1) return DAS_ERR_UNSUPPORTED;                                                 \
+        if (occ__ > ctas_per_sm) occ__ = ctas_per_sm;                                              \
+        const int grid__ = tiles < kNumSMs * occ__ ? tiles : kNumSMs * occ__;                      \
+        DAS_LAUNCH((mc_score_tma_kernel<C, P, Q>), grid__, kTmaThreads, smem, st, q);              \
     } while (0)
     if (probs && votes) DAS_TMA(true, true);
     else if (probs) DAS_TMA(true, false);

@@ -43,8 +43,13 @@ __device__ __forceinline__ void tma_mbar_wait(uint32_t bar, uint32_t parity) {
         : "memory");
 }
 
+// CTAs per SM: 3 x 160 threads at 128 registers for C <= 20, 2 x 160 at up to 200 registers for more classes.
+// (__maxnreg__(136) removes the last 16-byte spill at C = 19 but the per-warp register allocation granularity
+// then only fits 2 CTAs per SM: measured 0.85 instead of 0.96 of the HBM peak.)
+constexpr int tma_ctas_per_sm(int C) { return C <= 20 ? 3 : 2; }
+
 template <int C, bool PROBS, bool VOTES>
-__global__ void __launch_bounds__(kTmaThreads, 3) mc_score_tma_kernel(const __grid_constant__ McTmaParams q) {
+__global__ void __launch_bounds__(kTmaThreads, tma_ctas_per_sm(C)) mc_score_tma_kernel(const __grid_constant__ McTmaParams q) {
     constexpr int NT = 128, VEC = 2;
     constexpr uint32_t kStageBytes = (uint32_t)C * kTmaPix * sizeof(float);
     extern __shared__ __align__(1024) uint8_t ring[];
