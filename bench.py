@@ -49,6 +49,9 @@ def parse():
     ap.add_argument("--mode", default="full", choices=["full", "votes", "probs"],
                     help="full = vote entropy + softmax scores (default); votes = the reference's vote entropy only; "
                          "probs = softmax-mean entropy / BALD / confidence / margin only")
+    ap.add_argument("--workload", default="cityscapes", choices=["cityscapes", "pascal"],
+                    help="cityscapes = BASELINE config 2 (default, the metric's config); pascal = config 4 shape: "
+                         "513x513, C=21, T=20, pool 10582, top-60 (odd planes: flat 1-D TMA maps)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
@@ -391,6 +394,10 @@ def run_reference(args):
 
 if __name__ == "__main__":
     a = parse()
+    if a.workload == "pascal":
+        H, W, C, T = 513, 513, 21, 20
+        POOL_IMAGES, TOPK = 10582, 60
+        WORKLOAD = "ceal_mc_noise_pascal_pool_513x513_c21_t20"
     if a.impl == "reference":
         run_reference(a)
     else:

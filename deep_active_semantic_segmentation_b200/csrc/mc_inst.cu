@@ -136,22 +136,28 @@ int launch_score_tma(const McTmaParams& p, int flags, int ctas_per_sm, cudaStrea
     const size_t smem = stage * stages;
     const int tiles = p.B * p.tiles_per_image;
     // persistent grid = what is actually co-resident (registers can allow fewer CTAs than shared memory does)
-#define DAS_TMA(P, Q)                                                                              \
+#define DAS_TMA(P, Q, A)                                                                           \
     do {                                                                                           \
-        int rc__ = set_smem(mc_score_tma_kernel<C, P, Q>, smem);                                   \
+        int rc__ = set_smem(mc_score_tma_kernel<C, P, Q, A>, smem);                                \
         if (rc__ != DAS_OK) return rc__;                                                           \
         int occ__ = 0;                                                                             \
         cudaError_t e__ = cudaOccupancyMaxActiveBlocksPerMultiprocessor(                           \
-            &occ__, mc_score_tma_kernel<C, P, Q>, kTmaThreads, smem);                              \
+            &occ__, mc_score_tma_kernel<C, P, Q, A>, kTmaThreads, smem);                           \
         if (e__ != cudaSuccess) return cuda_fail(e__);                                             \
         if (occ__ < 1) return DAS_ERR_UNSUPPORTED;                                                 \
         if (occ__ > ctas_per_sm) occ__ = ctas_per_sm;                                              \
         const int grid__ = tiles < kNumSMs * occ__ ? tiles : kNumSMs * occ__;                      \
-        DAS_LAUNCH((mc_score_tma_kernel<C, P, Q>), grid__, kTmaThreads, smem, st, q);              \
+        DAS_LAUNCH((mc_score_tma_kernel<C, P, Q, A>), grid__, kTmaThreads, smem, st, q);           \
     } while (0)
-    if (probs && votes) DAS_TMA(true, true);
-    else if (probs) DAS_TMA(true, false);
-    else DAS_TMA(false, true);
+    if (!p.flat) {
+        if (probs && votes) DAS_TMA(true, true, false);
+        else if (probs) DAS_TMA(true, false, false);
+        else DAS_TMA(false, true, false);
+    } else {
+        if (probs && votes) DAS_TMA(true, true, true);
+        else if (probs) DAS_TMA(true, false, true);
+        else DAS_TMA(false, true, true);
+    }
 #undef DAS_TMA
     DAS_CHECK_LAUNCH();
     return DAS_OK;
