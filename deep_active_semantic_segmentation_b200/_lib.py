@@ -17,6 +17,7 @@ MC_PROBS = 2
 MC_SINGLE_SHOT = 4
 N_SCORES = 6
 SCORE_INDEX = {"vote_entropy": 0, "pred_entropy": 1, "bald": 2, "confidence": 3, "margin": 4, "expected_entropy": 5}
+ACC_INDEX = {"wrong_count": 0, "p0_sum": 1, "not_argmax_sum": 2, "unsure_mean": 3, "valid_count": 4}
 MAX_CLASSES = 32
 MAX_PASSES = 255
 MAX_PASS_GROUP = 32
@@ -51,7 +52,11 @@ _PROTOTYPES = {
     "das_minmax_init": (_i, [_vp, _vp]),
     "das_box_sum": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "das_minmax_normalise": (_i, [_vp, _sz, _vp, _vp]),
-    "das_nms_sequences": (_i, [_vp, _i, _i, _i, _i, _i, _f, _vp, _vp, _vp, _vp]),
+    "das_nms_sequences": (_i, [_vp, _i, _i, _i, _i, _i, _f, _vp, _vp, _vp, C.c_longlong, _vp, _vp]),
+    "das_accuracy_workspace_bytes": (_i, [_i, _i, _i, C.POINTER(_sz)]),
+    "das_accuracy_scores": (_i, [_vp, _i, _i, _i, _i, _vp, _i, _vp, _vp, _vp, _vp]),
+    "das_maxsubset_workspace_bytes": (_i, [_i, _i, _i, _i, C.POINTER(_sz)]),
+    "das_maxsubset_greedy": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
     "das_topk_workspace_bytes": (_i, [_i, _i, C.POINTER(_sz)]),
     "das_topk": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "das_kcenter_filter_bytes": (_i, [_i, _i, _i, C.POINTER(_sz)]),

@@ -1,7 +1,9 @@
 """Drop-in mirror of the reference's `active_selection` package for the scoring hot path
 (reference active_selection/__init__.py:9-25).  Same factory, same class names."""
+from .accuracy import ActiveSelectionAccuracy
 from .ceal import ActiveSelectionCEAL
 from .core_set import ActiveSelectionCoreSet
+from .max_subset import ActiveSelectionMaxSubset
 from .mc_dropout import ActiveSelectionMCDropout
 from .mc_noise import ActiveSelectionMCNoise
 
@@ -19,6 +21,11 @@ def get_active_selection_class(active_selection_method, dataset_num_classes, dat
         return ActiveSelectionMCNoise(dataset_num_classes, dataset_lmdb_env, crop_size, dataloader_batch_size)
     if active_selection_method in _VARIANCE:
         return ActiveSelectionMCDropout(dataset_num_classes, dataset_lmdb_env, crop_size, dataloader_batch_size)
-    # 'accuracy_labels' / 'accuracy_eval' (accuracy-predictor selectors) and the max-subset selector are
-    # outside the scoring hot path; like any unknown method they raise here.
+    if active_selection_method in ('accuracy_labels', 'accuracy_eval'):
+        return ActiveSelectionAccuracy(dataset_num_classes, dataset_lmdb_env, crop_size, dataloader_batch_size)
     raise NotImplementedError(active_selection_method)
+
+
+def get_max_subset_active_selector(dataset_lmdb_env, crop_size, dataloader_batch_size):
+    # reference active_selection/__init__.py:24-25
+    return ActiveSelectionMaxSubset(dataset_lmdb_env, crop_size, dataloader_batch_size)

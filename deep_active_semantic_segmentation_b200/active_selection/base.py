@@ -12,7 +12,7 @@ from torch.utils.data import DataLoader
 
 from .. import constants as _own_constants
 from .. import dist, ops
-from .._lib import MAX_PASS_GROUP, SCORE_INDEX, DasError
+from .._lib import MAX_PASS_GROUP, SCORE_INDEX, TOPK_MAX_K, DasError
 
 # The reference selectors reach the data layer through the module attribute
 # `paths_dataset.PathsDataset` (mc_dropout.py:131, ceal.py:21, core_set.py:42).  The data layer is out
@@ -140,12 +140,40 @@ def region_tail(selector, score_maps, images, lo, region_size, selection_size):
     mm = dist.allreduce_minmax(selector._minmax)
     ops.minmax_normalise(score_maps, mm)
     kmax = max(1, min(math.ceil(num_requested), ops.nms_pick_bound(H2, W2, region_size)))
-    cs, rc, cnt = ops.nms_sequences(score_maps, region_size, kmax, 0.01)
-    cs, rc, cnt = cs.cpu(), rc.cpu(), cnt.cpu().tolist()
-    local = [[(cs[i, j].item(), int(rc[i, j, 0]), int(rc[i, j, 1])) for j in range(cnt[i])] for i in range(N_local)]
-    seqs = []
-    for part in dist.gather_objects(local):
-        seqs += part
-    regions, count = dist.merge_nms_sequences(seqs, region_size, num_requested, H2, W2)
+    regions, count = global_nms(score_maps, lo, len(images), region_size, num_requested, kmax)
     new_regions = {images[i]: regions[i] for i in range(len(regions)) if regions[i]}
     return new_regions, count
+
+
+def global_nms(score_maps, lo, n_images, region_size, max_selection_count, kmax):
+    """The pool-global greedy NMS of mc_dropout.py:82-108 from image-local device sequences.
+
+    Picks of one image are sorted by (score desc, flat index asc), so the reference's loop - repeat
+    {global first arg-max; zero its window} - visits the candidates of all images in exactly that order: a K3
+    top-k over the flattened candidate table (ties keep table order = flat order), an all-gather of each
+    rank's head, and the stop rule (`count < ceil(K)`, pool max >= 0.01 checked after each pick) on the merged
+    prefix.  Only the <= ceil(K) winners ever leave the device."""
+    import numpy as np
+
+    N_local, H2, W2 = score_maps.shape
+    want = math.ceil(max_selection_count)
+    if want > TOPK_MAX_K:       # more picks than one K3 launch ranks: k-way merge of the sequences on the host
+        cs, rc, cnt = ops.nms_sequences(score_maps, region_size, kmax, 0.01)
+        seqs = []
+        for part in dist.gather_objects(dist.sequences_from_device(cs, rc, cnt)):
+            seqs += part
+        return dist.merge_nms_sequences(seqs, region_size, max_selection_count, H2, W2)
+    cs, rc, cnt, flat = ops.nms_sequences(score_maps, region_size, kmax, 0.01, image_offset=lo, with_flat=True)
+    s, ids = ops.topk(cs.reshape(-1), min(want, cs.numel()), True, ids=flat.reshape(-1))
+    gs, gi = dist.gather_ranked_np(s, ids, max(want, 1), True)
+    # stop rule on the merged prefix: candidates exist (id >= 0, score > -inf), at most `want` picks, and every
+    # pick after the first needs score >= 0.01 (the pool maximum the reference checks after the previous pick)
+    ok = (gi >= 0) & np.isfinite(gs)
+    ok[1:] &= gs[1:] >= np.float32(0.01)
+    count = int(len(ok) if ok.all() else np.argmin(ok))
+    img, rem = np.divmod(gi[:count], H2 * W2)
+    r, c = np.divmod(rem, W2)
+    regions = [[] for _ in range(n_images)]
+    for i_, r_, c_ in zip(img.tolist(), r.tolist(), c.tolist()):
+        regions[i_].append((r_, c_, region_size, region_size))
+    return regions, count

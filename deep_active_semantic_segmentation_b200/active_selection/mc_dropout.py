@@ -47,10 +47,7 @@ class ActiveSelectionMCDropout(ActiveSelectionBase):
         dev_maps = score_maps if score_maps.is_cuda else score_maps.cuda()
         dev_maps = dev_maps.contiguous()
         kmax = max(1, min(math.ceil(max_selection_count), ops.nms_pick_bound(H2, W2, region_size)))
-        cs, rc, cnt = ops.nms_sequences(dev_maps, region_size, kmax, 0.01)
-        cs, rc, cnt = cs.cpu(), rc.cpu(), cnt.cpu().tolist()
-        seqs = [[(cs[i, j].item(), int(rc[i, j, 0]), int(rc[i, j, 1])) for j in range(cnt[i])] for i in range(N)]
-        regions, count = dist.merge_nms_sequences(seqs, region_size, max_selection_count, H2, W2)
+        regions, count = base.global_nms(dev_maps, 0, N, region_size, max_selection_count, kmax)
         # leave the caller's tensor in the state the reference leaves it in: chosen windows zeroed
         for i, lst in enumerate(regions):
             for (r, c, _, _) in lst:

@@ -155,7 +155,8 @@ __global__ void minmax_normalise_kernel(float* x, size_t n, const float* minmax)
 constexpr int kNmsThreads = 512;
 __global__ void __launch_bounds__(kNmsThreads) nms_sequences_kernel(float* score_maps, int H2, int W2, int R, int kmax,
                                                                     float stop, float* cand_score, int32_t* cand_rc,
-                                                                    int32_t* cand_count) {
+                                                                    int32_t* cand_count, long long image_offset,
+                                                                    int64_t* cand_flat) {
     __shared__ unsigned long long wbest[kNmsThreads / 32];
     __shared__ unsigned long long best_s;
     const int img = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -185,6 +186,8 @@ __global__ void __launch_bounds__(kNmsThreads) nms_sequences_kernel(float* score
             cand_score[(size_t)img * kmax + picks] = s;
             cand_rc[((size_t)img * kmax + picks) * 2 + 0] = r;
             cand_rc[((size_t)img * kmax + picks) * 2 + 1] = c;
+            if (cand_flat != nullptr)  // flat index in the un-sharded pool: the reference's arg-max tie rule
+                cand_flat[(size_t)img * kmax + picks] = ((image_offset + img) * H2 + r) * (long long)W2 + c;
         }
         ++picks;
         const int r0 = max(0, r - R), r1 = min(H2, r + R), c0 = max(0, c - R), c1 = min(W2, c + R);
@@ -193,6 +196,11 @@ __global__ void __launch_bounds__(kNmsThreads) nms_sequences_kernel(float* score
         __syncthreads();
     }
     if (tid == 0) cand_count[img] = picks;
+    // unused slots rank below every real candidate (das_topk over the flattened table)
+    for (int j = picks + tid; j < kmax; j += kNmsThreads) {
+        cand_score[(size_t)img * kmax + j] = -INFINITY;
+        if (cand_flat != nullptr) cand_flat[(size_t)img * kmax + j] = -1;
+    }
 }
 
 }  // namespace das
@@ -261,13 +269,14 @@ int das_minmax_normalise(float* score_maps, size_t n, const float* minmax, void*
 }
 
 int das_nms_sequences(float* score_maps, int N, int H2, int W2, int R, int kmax, float stop, float* cand_score,
-                      int32_t* cand_rc, int32_t* cand_count, void* stream) {
+                      int32_t* cand_rc, int32_t* cand_count, long long image_offset, int64_t* cand_flat, void* stream) {
     if (score_maps == nullptr || cand_score == nullptr || cand_rc == nullptr || cand_count == nullptr)
         return DAS_ERR_INVALID_ARG;
     if (N <= 0 || H2 <= 0 || W2 <= 0 || R <= 0 || kmax <= 0) return DAS_ERR_INVALID_ARG;
     if ((long long)H2 * W2 > 0x7fffffffLL) return DAS_ERR_UNSUPPORTED;
+    if (image_offset < 0) return DAS_ERR_INVALID_ARG;
     DAS_LAUNCH(nms_sequences_kernel, N, kNmsThreads, 0, (cudaStream_t)stream, score_maps, H2, W2, R, kmax, stop,
-               cand_score, cand_rc, cand_count);
+               cand_score, cand_rc, cand_count, image_offset, cand_flat);
     DAS_CHECK_LAUNCH();
     return DAS_OK;
 }

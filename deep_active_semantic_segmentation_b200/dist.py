@@ -74,6 +74,34 @@ def merge_ranked(scores, ids, k: int, descending: bool):
     return [scores[j] for j in order], [ids[j] for j in order]
 
 
+def gather_ranked_np(scores, ids, k: int, descending: bool = True):
+    """numpy twin of gather_candidates + merge_ranked for large k (region candidates): every rank's head of at
+    most k (score, global id) pairs, already sorted, -> the first k of their stable merge as (float32 [m],
+    int64 [m]) arrays.  Order: score, then global id ascending (the reference's first-arg-max tie rule)."""
+    import numpy as np
+
+    W, _ = world()
+    s = scores.detach().to(torch.float32).reshape(-1)
+    i = ids.detach().to(torch.int64).reshape(-1)
+    if W == 1:
+        return s.cpu().numpy()[:k], i.cpu().numpy()[:k]      # one rank: K3 already produced this order
+    dev = _comm_device()
+    buf_s = torch.full((k,), float("-inf") if descending else float("inf"), dtype=torch.float32, device=dev)
+    buf_i = torch.full((k,), -1, dtype=torch.int64, device=dev)
+    buf_s[: s.numel()] = s.to(dev)
+    buf_i[: i.numel()] = i.to(dev)
+    all_s = [torch.empty_like(buf_s) for _ in range(W)]
+    all_i = [torch.empty_like(buf_i) for _ in range(W)]
+    td.all_gather(all_s, buf_s)
+    td.all_gather(all_i, buf_i)
+    gs = torch.cat(all_s).cpu().numpy()
+    gi = torch.cat(all_i).cpu().numpy()
+    keep = gi >= 0
+    gs, gi = gs[keep], gi[keep]
+    order = np.lexsort((gi, -gs if descending else gs))[:k]
+    return gs[order], gi[order]
+
+
 def allreduce_minmax(minmax: torch.Tensor) -> torch.Tensor:
     """Pool-global min / max from the per-rank (min, max) pair."""
     W, _ = world()
@@ -93,6 +121,15 @@ def gather_objects(obj):
     out = [None] * W
     td.all_gather_object(out, obj)
     return out
+
+
+def sequences_from_device(cand_score, cand_rc, cand_count):
+    """(scores [N,kmax], rc [N,kmax,2], count [N]) device tensors of das_nms_sequences -> list over images of
+    [(score, r, c), ...] in pick order.  One D2H copy per tensor, no per-candidate synchronisation."""
+    cs = cand_score.detach().cpu().numpy()
+    rc = cand_rc.detach().cpu().numpy()
+    cnt = cand_count.detach().cpu().numpy()
+    return [[(cs[i, j], int(rc[i, j, 0]), int(rc[i, j, 1])) for j in range(int(cnt[i]))] for i in range(cs.shape[0])]
 
 
 def merge_nms_sequences(seqs, region_size: int, max_selection_count: float, H2: int, W2: int, stop: float = 0.01):

@@ -208,19 +208,72 @@ def nms_pick_bound(H2: int, W2: int, R: int) -> int:
     return math.ceil(H2 / R) * math.ceil(W2 / R)
 
 
-def nms_sequences(score_maps: torch.Tensor, R: int, kmax: int, stop: float = 0.01):
-    """Per-image greedy NMS sequences; MUTATES score_maps. -> (scores [N,kmax], rc [N,kmax,2], count [N])."""
+def nms_sequences(score_maps: torch.Tensor, R: int, kmax: int, stop: float = 0.01, image_offset: int = 0,
+                  with_flat: bool = False):
+    """Per-image greedy NMS sequences; MUTATES score_maps. -> (scores [N,kmax], rc [N,kmax,2], count [N])
+    (+ flat int64 [N,kmax] pool indices with with_flat=True).  Unused score slots are -inf."""
     if not score_maps.is_contiguous():
         raise DasError("nms_sequences: score_maps must be contiguous (modified in place)")
     _need_cuda(score_maps, "score_maps", torch.float32)
     N, H2, W2 = score_maps.shape
     dev = score_maps.device
-    cs = torch.zeros((N, kmax), dtype=torch.float32, device=dev)
+    cs = torch.empty((N, kmax), dtype=torch.float32, device=dev)
     rc = torch.zeros((N, kmax, 2), dtype=torch.int32, device=dev)
     cnt = torch.zeros((N,), dtype=torch.int32, device=dev)
+    flat = torch.empty((N, kmax), dtype=torch.int64, device=dev) if with_flat else None
     check(_lib.load().das_nms_sequences(_ptr(score_maps), N, H2, W2, R, kmax, C.c_float(stop), _ptr(cs), _ptr(rc),
-                                        _ptr(cnt), _stream()), "das_nms_sequences")
+                                        _ptr(cnt), int(image_offset), _ptr(flat), _stream()), "das_nms_sequences")
+    if with_flat:
+        return cs, rc, cnt, flat
     return cs, rc, cnt
+
+
+# ---------------------------------------------------------------------------------------------
+# accuracy-predictor selectors
+# ---------------------------------------------------------------------------------------------
+
+def accuracy_scores(logits: torch.Tensor, labels: torch.Tensor | None, num_classes: int, p0_map: bool = False):
+    """logits f32 [B,C,H,W], labels f32 [B,H,W] -> scores f32 [B,5] (column order _lib.ACC_INDEX)
+    [+ softmax[0] map with invalid pixels zeroed, f32 [B,H,W]] (accuracy.py:30-33,55-64,117-118,159-162)."""
+    logits = _need_cuda(logits, "logits", torch.float32)
+    B, Cc, H, W = logits.shape
+    if labels is not None:
+        labels = _need_cuda(labels, "labels", torch.float32)
+        if tuple(labels.shape) != (B, H, W):
+            raise DasError(f"labels shape {tuple(labels.shape)} != {(B, H, W)}")
+    lib = _lib.load()
+    nbytes = C.c_size_t()
+    check(lib.das_accuracy_workspace_bytes(B, H, W, C.byref(nbytes)), "das_accuracy_workspace_bytes")
+    ws = torch.empty(nbytes.value, dtype=torch.uint8, device=logits.device)
+    scores = torch.empty((B, len(_lib.ACC_INDEX)), dtype=torch.float32, device=logits.device)
+    pm = torch.empty((B, H, W), dtype=torch.float32, device=logits.device) if p0_map else None
+    check(lib.das_accuracy_scores(_ptr(logits), B, Cc, H, W, _ptr(labels), int(num_classes), _ptr(pm), _ptr(scores),
+                                  _ptr(ws), _stream()), "das_accuracy_scores")
+    return (scores, pm) if p0_map else scores
+
+
+# ---------------------------------------------------------------------------------------------
+# max-subset representativeness
+# ---------------------------------------------------------------------------------------------
+
+def maxsubset_greedy(X: torch.Tensor, Y: torch.Tensor, k: int) -> torch.Tensor:
+    """Greedy facility location (max_subset.py:17-39): X [N,D] pool, Y [M,D] candidates (both float32 or both
+    float64, CUDA) -> int32 [k] candidate indices in pick order."""
+    if X.dtype != Y.dtype or X.dtype not in (torch.float32, torch.float64):
+        raise DasError("maxsubset_greedy: X and Y must both be float32 or both float64")
+    X, Y = _need_cuda(X, "X", X.dtype), _need_cuda(Y, "Y", Y.dtype)
+    (N, D), (M, D2) = X.shape, Y.shape
+    if D != D2:
+        raise DasError("maxsubset_greedy: feature dimensions differ")
+    f64 = 1 if X.dtype == torch.float64 else 0
+    lib = _lib.load()
+    nbytes = C.c_size_t()
+    check(lib.das_maxsubset_workspace_bytes(N, M, D, f64, C.byref(nbytes)), "das_maxsubset_workspace_bytes")
+    ws = torch.empty(nbytes.value, dtype=torch.uint8, device=X.device)
+    picks = torch.empty(max(k, 1), dtype=torch.int32, device=X.device)
+    check(lib.das_maxsubset_greedy(_ptr(X), _ptr(Y), N, M, D, f64, int(k), _ptr(picks), _ptr(ws), _stream()),
+          "das_maxsubset_greedy")
+    return picks[:k]
 
 
 # ---------------------------------------------------------------------------------------------

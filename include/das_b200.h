@@ -164,11 +164,52 @@ int das_minmax_normalise(float* score_maps, size_t n, const float* minmax, void*
  * ActiveSelectionMCDropout.square_nms (mc_dropout.py:82-108).  For each of the N images (one CTA
  * each): repeat { first flat argmax (r,c); record; zero [r-R,r+R) x [c-R,c+R) } while picks < kmax
  * and (it is the first pick or the map max >= stop).  MUTATES score_maps like the reference.
- * cand_score f32 [N,kmax], cand_rc int32 [N,kmax,2], cand_count int32 [N].
- * The global selection is the (score desc, flat index asc) merge of these sequences with the
- * reference's stop rule - see active_selection/mc_dropout.py in the Python mirror. */
+ * cand_score f32 [N,kmax] (unused slots = -inf), cand_rc int32 [N,kmax,2], cand_count int32 [N],
+ * cand_flat int64 [N,kmax] or NULL: ((image_offset + i) * H2 + r) * W2 + c, the flat index of the pick in the
+ *   un-sharded pool (-1 in unused slots).
+ * Within an image the picks are sorted by (score desc, flat index asc), so the reference's global greedy loop is
+ * exactly: das_topk over the flattened cand_score table (ties keep table order = flat order) and the stop rule
+ * of mc_dropout.py:87,105 on that prefix - see active_selection/base.py:region_tail in the Python mirror. */
 int das_nms_sequences(float* score_maps, int N, int H2, int W2, int R, int kmax, float stop,
-                      float* cand_score, int32_t* cand_rc, int32_t* cand_count, void* stream);
+                      float* cand_score, int32_t* cand_rc, int32_t* cand_count, long long image_offset,
+                      int64_t* cand_flat, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Accuracy-predictor selectors (active_selection/accuracy.py)
+ * One pass over logits f32 [B,C,H,W] (the segmentation output, or the C = 2 error-predictor head) and the
+ * float32 labels.  A pixel is valid iff 0 <= label < num_classes (accuracy.py:31,56,116); labels == NULL:
+ * every pixel valid and wrong_count = 0.  image_scores f32 [B, DAS_ACC_N]:
+ *   DAS_ACC_WRONG_COUNT     sum_valid [label != argmax_c logits]                accuracy.py:30-33
+ *   DAS_ACC_P0_SUM          sum_valid softmax(logits)[0]                        accuracy.py:55-58
+ *   DAS_ACC_NOT_ARGMAX_SUM  sum_valid (1 - argmax_c logits)                     accuracy.py:60-64
+ *   DAS_ACC_UNSURE_MEAN     mean_valid (4 p1 - 4 p1^2), p1 = softmax[1]         accuracy.py:117-118 (NaN if none valid)
+ *   DAS_ACC_VALID_COUNT     number of valid pixels
+ * p0_map f32 [B,H,W] or NULL: softmax[0] with invalid pixels = 0 (accuracy.py:159-162), the input of the region
+ * tail (das_suppress_rects -> das_box_sum -> das_minmax_normalise -> das_nms_sequences).
+ * ------------------------------------------------------------------------------------------ */
+enum {
+    DAS_ACC_WRONG_COUNT = 0,
+    DAS_ACC_P0_SUM = 1,
+    DAS_ACC_NOT_ARGMAX_SUM = 2,
+    DAS_ACC_UNSURE_MEAN = 3,
+    DAS_ACC_VALID_COUNT = 4,
+    DAS_ACC_N = 5
+};
+int das_accuracy_workspace_bytes(int B, int H, int W, size_t* bytes);
+int das_accuracy_scores(const float* logits, int B, int C, int H, int W, const float* labels, int num_classes,
+                        float* p0_map, float* image_scores, void* workspace, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Max-subset representativeness (active_selection/max_subset.py:17-39)
+ * Greedy facility location: D[n,i] = ||x_n - y_i|| (float64 arithmetic; stored as float32 for float32 features,
+ * as sklearn.pairwise_distances returns them), then k times: the FIRST unselected candidate i minimising
+ * sum_n min(min_d[n], D[n,i]) (the reference maximises the negated sum with a strict '>'), min_d = min(min_d, D[:,i]).
+ * X [N,D] pool features, Y [M,D] candidate features, both float32 (is_f64 = 0) or float64 (1), device, row major.
+ * picks: device int32 [k] candidate indices in pick order (-1 once every candidate is taken).
+ * ------------------------------------------------------------------------------------------ */
+int das_maxsubset_workspace_bytes(int N, int M, int D, int is_f64, size_t* bytes);
+int das_maxsubset_greedy(const void* X, const void* Y, int N, int M, int D, int is_f64, int k, int32_t* picks,
+                         void* workspace, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Ranking  (K3)

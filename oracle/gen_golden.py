@@ -169,6 +169,97 @@ def gen_region(name, seed, N, T, C, S, block, R, selection_size, batch_size):
     print(f"[golden] {name}: {count} regions over {len(regions)} images, K={recorded['K']:.2f}")
 
 
+def unet_head(seed, N, S):
+    """Synthetic 2-channel error-predictor logits [N,2,S,S]: smooth blobs + noise (deterministic)."""
+    rng = np.random.Generator(np.random.Philox(key=[int(seed), 911]))
+    coarse = rng.standard_normal(size=(N, 2, -(-S // 8), -(-S // 8)), dtype=np.float32) * np.float32(2.0)
+    up = np.repeat(np.repeat(coarse, 8, axis=2), 8, axis=3)[:, :, :S, :S]
+    return (up + rng.standard_normal(size=(N, 2, S, S), dtype=np.float32)).astype(np.float32)
+
+
+def gen_accuracy(name, seed, N, C, S, block, R, k, batch_size):
+    """ActiveSelectionAccuracy (accuracy.py): label-based error count, softmax / argmax error mass of the
+    2-channel error head, 'unsure' score and the least-accurate region maps."""
+    ref = ref_shim.load_reference()
+    torch = ref.torch
+    from active_selection import accuracy as ref_accuracy  # reference module
+
+    pool = make_pool(seed, N, 1, C, S, S, block)
+    unet = unet_head(seed, N, S)
+    paths = [str(i) for i in range(N)]
+
+    class PairModel(torch.nn.Module):          # returns the segmentation logits or (deeplab_output, unet_output)
+        def __init__(self, pair):
+            super().__init__()
+            self.pair = pair
+
+        @property
+        def module(self):
+            return self
+
+        def forward(self, x):
+            gs = [int(round(float(v) / ref_shim.GID_SCALE)) for v in x[:, 0, 0, 0]]
+            seg = torch.from_numpy(np.stack([pool.logits[g, 0] for g in gs]))
+            if not self.pair:
+                return seg
+            return seg, torch.from_numpy(np.stack([unet[g] for g in gs]))
+
+    sel = ref.active_selection.get_active_selection_class("accuracy_labels", C, pool, S, batch_size)
+    out = {}
+    for key, call in (("labels", lambda: sel.get_least_accurate_sample_using_labels(PairModel(False), paths, k)),
+                      ("softmax", lambda: sel.get_least_accurate_samples(PairModel(True), paths, k, mode='softmax')),
+                      ("argmax", lambda: sel.get_least_accurate_samples(PairModel(True), paths, k, mode='argmax')),
+                      ("unsure", lambda: sel.get_unsure_samples(PairModel(True), paths, k))):
+        cap = SortedCapture()
+        ref_accuracy.sorted = cap
+        chosen = call()
+        del ref_accuracy.sorted
+        out[key + "_scores"] = np.array(cap.calls[0][0], dtype=np.float32)
+        out[key + "_selected"] = paths_to_idx(chosen)
+
+    rng = np.random.default_rng(seed + 1)
+    existing = [[] if i % 2 == 0 else [(int(rng.integers(0, S - R)), int(rng.integers(0, S - R)), R, R)] for i in range(N)]
+    regions, count = sel.get_least_accurate_region_maps(PairModel(True), paths, existing, R, 1)
+    ex_rows = np.array([(i, *rc) for i, lst in enumerate(existing) for rc in lst], dtype=np.int64).reshape(-1, 5)
+    np.savez_compressed(
+        os.path.join(GOLDEN, name + ".npz"),
+        meta=np.array([seed, N, C, S, block, R, k, batch_size], dtype=np.int64), versions=versions(),
+        logits_sha=np.array(checksum(pool.logits)), unet_sha=np.array(checksum(unet)),
+        existing=ex_rows, regions=regions_to_array(regions, N), count=np.int64(count), **out)
+    print(f"[golden] {name}: labels={out['labels_scores'][:4]} softmax={out['softmax_scores'][:3]} regions={count}")
+
+
+def gen_maxsubset():
+    """ActiveSelectionMaxSubset._max_representative_samples (max_subset.py:17-39): the reference's own seeded
+    fixture (tests.py:616-645, seed 27, 1000 x 1024 float64, 8 candidates, 4 picks) and two float32 pools with
+    duplicated candidates (np.random.randint draws with replacement in the reference's caller too)."""
+    ref_shim.load_reference()
+    from active_selection.max_subset import ActiveSelectionMaxSubset  # reference class
+
+    sel = ActiveSelectionMaxSubset(None, None, None)
+    np.random.seed(seed=27)
+    images = np.concatenate((np.random.normal(loc=2.0, scale=1.0, size=(400, 1024)),
+                             np.random.normal(loc=4.0, scale=1.0, size=(400, 1024)),
+                             np.random.normal(loc=6.0, scale=1.0, size=(150, 1024)),
+                             np.random.normal(loc=4.0, scale=3.0, size=(50, 1024))), axis=0)
+    cand = list(np.random.randint(0, len(images), 8))
+    ref_picks = sel._max_representative_samples(list(images), list(images[cand, :]), 4)
+    out = {"ref_seed": np.int64(27), "ref_candidates": np.array(cand, dtype=np.int64),
+           "ref_picks": np.array(ref_picks, dtype=np.int64), "ref_images_sha": np.array(checksum(images))}
+    for tag, seed, N, M, D, k in (("a", 5, 600, 40, 96, 20), ("b", 6, 1500, 120, 304, 60)):
+        X = synth.coreset_features(seed, N, D)
+        rng = np.random.default_rng(seed)
+        ci = rng.integers(0, N, size=M)                 # with replacement: duplicates happen
+        Y = (X[ci] + np.float32(0.05) * rng.standard_normal((M, D)).astype(np.float32)).astype(np.float32)
+        Y[M // 3] = Y[M // 5]                            # one exact duplicate pair
+        picks = sel._max_representative_samples(list(X), list(Y), k)
+        out[f"{tag}_meta"] = np.array([seed, N, M, D, k], dtype=np.int64)
+        out[f"{tag}_picks"] = np.array(picks, dtype=np.int64)
+        out[f"{tag}_x_sha"], out[f"{tag}_y_sha"] = np.array(checksum(X)), np.array(checksum(Y))
+    np.savez_compressed(os.path.join(GOLDEN, "maxsubset.npz"), versions=versions(), **out)
+    print(f"[golden] maxsubset: reference fixture picks {ref_picks} of candidates {cand}; a={out['a_picks'][:6]} b={out['b_picks'][:6]}")
+
+
 def gen_noise(name, seed, N, T, C, S, block, R, k, batch_size):
     """mc_noise.py: input-noise / feature-noise / noise+dropout image scores and its region maps."""
     ref = ref_shim.load_reference()
@@ -284,6 +375,8 @@ FIXTURES = {
     "coreset_mid": lambda: gen_coreset("coreset_mid", synth.DEFAULT_SEED + 7, N=1500, D=2736, L=50, K=60),
     "coreset_e2e": lambda: gen_coreset_e2e("coreset_e2e", synth.DEFAULT_SEED + 8, N=14, L=4, K=5, batch_size=4),
     "nms_png": gen_nms_png,
+    "maxsubset": gen_maxsubset,
+    "accuracy_small": lambda: gen_accuracy("accuracy_small", 41, 6, 5, 40, 8, 9, 4, 3),
 }
 
 

@@ -293,3 +293,63 @@ def avg_pool_features(feat: np.ndarray, k: int) -> np.ndarray:
         for j in range(ow):
             out[:, i, j] = feat[:, i * s:i * s + k, j * s:j * s + k].mean(axis=(1, 2), dtype=np.float64)
     return out.reshape(-1)
+
+
+# --------------------------------------------------------------------------------------
+# accuracy-predictor selectors (active_selection/accuracy.py)
+# --------------------------------------------------------------------------------------
+
+def accuracy_scores(seg_logits, unet_logits, labels: np.ndarray, num_classes: int) -> dict:
+    """Per-image scores of ActiveSelectionAccuracy for one image.
+    seg_logits [C,H,W] or None: wrong_count = #valid pixels with label != argmax (accuracy.py:30-33).
+    unet_logits [2,H,W] or None: p0_sum = sum_valid softmax[0] (:55-58); not_argmax_sum = sum_valid (1 - argmax)
+    (:60-64); unsure_mean = mean_valid (4 p1 - 4 p1^2) (:117-118).  valid = 0 <= label < num_classes."""
+    valid = (labels >= 0) & (labels < num_classes)
+    out = {"valid_count": np.float32(valid.sum())}
+    if seg_logits is not None:
+        pred = np.argmax(seg_logits, axis=0).astype(np.float32)
+        out["wrong_count"] = np.float32((labels[valid] != pred[valid]).sum())
+    if unet_logits is not None:
+        p = softmax_classes(unet_logits)
+        out["p0_sum"] = np.float32(p[0][valid].astype(np.float32).sum(dtype=np.float32))
+        out["not_argmax_sum"] = np.float32((np.float32(1) - np.argmax(unet_logits, axis=0).astype(np.float32))[valid].sum(dtype=np.float32))
+        p1 = p[1][valid].astype(np.float32)
+        y = np.float32(4) * p1 - np.float32(4) * p1 ** 2
+        out["unsure_mean"] = np.float32(y.mean(dtype=np.float32)) if y.size else np.float32(np.nan)
+    return out
+
+
+def accuracy_error_map(unet_logits: np.ndarray, labels: np.ndarray, num_classes: int) -> np.ndarray:
+    """softmax[0] of the error head with invalid pixels zeroed (accuracy.py:159-162), float32 [H,W]."""
+    p0 = softmax_classes(unet_logits)[0].astype(np.float32).copy()
+    p0[(labels < 0) | (labels >= num_classes)] = 0
+    return p0
+
+
+# --------------------------------------------------------------------------------------
+# max-subset representativeness (active_selection/max_subset.py)
+# --------------------------------------------------------------------------------------
+
+def max_representative_samples(image_features, candidate_features, selection_count: int) -> list:
+    """Greedy facility location of max_subset.py:17-39.  D = sklearn pairwise_distances(X, Y) (euclidean; float32
+    inputs give float32 distances, float64 inputs float64); repeat selection_count times: for every not yet
+    selected candidate i, score_i = -sum_n min(min_d[n], D[n,i]); take the FIRST i with the strictly largest score;
+    min_d = min(min_d, D[:, i])."""
+    from sklearn.metrics import pairwise_distances
+
+    X, Y = np.asarray(image_features), np.asarray(candidate_features)
+    D = pairwise_distances(X, Y, metric="euclidean")
+    min_d = np.ones(len(X)) * float("inf")
+    selected = []
+    for _ in range(selection_count):
+        best, best_i, best_d = float("-inf"), None, None
+        for i in range(len(Y)):
+            if i in selected:
+                continue
+            tmp = np.minimum(min_d, D[:, i])
+            score = np.sum(tmp) * -1
+            if score > best:
+                best, best_i, best_d = score, i, tmp
+        selected.append(best_i)
+        min_d = best_d
+    return selected

@@ -208,3 +208,38 @@ def test_errors_are_loud():
         single.accumulate(torch.zeros(1, 5, 8, 8, device="cuda"))   # a single-shot state has no accumulators
     with pytest.raises(DasError):
         ops.MCState(1, 5, 8, 8, 33, single_shot=True)               # more passes than one launch can take
+
+
+@pytest.mark.parametrize("B,T,C,H,W", [(2, 6, 19, 32, 64), (3, 5, 21, 65, 65), (2, 4, 7, 33, 34), (1, 20, 19, 128, 256)])
+@pytest.mark.parametrize("probs,votes", [(True, True), (True, False)])
+def test_tma_ring_kernel_is_bit_identical_to_ldg_kernel(B, T, C, H, W, probs, votes, monkeypatch):
+    """The TMA-staged single-shot kernel (3-D maps for H*W % 4 == 0, flat shifted 1-D maps otherwise) and the LDG
+    kernel run the same per-pixel arithmetic: maps and votes must agree bit for bit, image scores to fp32 rounding
+    of the (differently partitioned) block partials."""
+    ops = _ops()
+    gs = list(range(B))
+    logits = synth.pool_logits(21, gs, T, C, H, W, 8)
+    labels = synth.pool_labels(21, gs, H, W, C, 8)
+    dev = [torch.from_numpy(np.ascontiguousarray(logits[:, t])).cuda() for t in range(T)]
+    lab = torch.from_numpy(labels).cuda()
+    maps = (["vote_entropy"] if votes else []) + [m for m in ops.MAP_NAMES if m != "vote_entropy"]
+    outs = {}
+    for tma in ("1", "0"):
+        monkeypatch.setenv("DAS_MC_TMA", tma)
+        n0 = _lib_launches()
+        st = ops.MCState(B, C, H, W, T, votes=votes, probs=probs, single_shot=True)
+        outs[tma] = st.score(dev, lab, maps=maps, scores=True, weak_labels=votes)
+        torch.cuda.synchronize()
+        assert _lib_launches() - n0 == 2
+    for k in maps + (["weak_labels"] if votes else []):
+        assert torch.equal(outs["1"][k], outs["0"][k]), k
+    a, b = outs["1"]["scores"].cpu().numpy(), outs["0"]["scores"].cpu().numpy()
+    np.testing.assert_allclose(a, b, rtol=2e-6, atol=1e-7, equal_nan=True)
+    for bi in range(B):            # and both agree with the oracle
+        o = R.mc_maps(logits[bi], labels[bi], C)
+        np.testing.assert_allclose(outs["1"]["pred_entropy"][bi].cpu().numpy(), o["pred_entropy"], rtol=1e-5, atol=2e-6)
+
+
+def _lib_launches():
+    from deep_active_semantic_segmentation_b200 import _lib
+    return _lib.launch_count()

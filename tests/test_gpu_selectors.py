@@ -165,3 +165,91 @@ def test_composed_mc_scores_and_factory_errors():
         _factory("no_such_method", C, pool, -1, 2)
     with pytest.raises(IndexError):
         sel.get_vote_entropy_for_images(fakes.ReplayModel(pool), [], 3)       # the reference fails the same way
+
+
+def test_accuracy_selectors_match_reference():
+    g = G.load("accuracy_small")
+    seed, N, C, S, block, Rg, k, bs = (int(v) for v in g["meta"])
+    logits, labels = G.pool_from_meta(seed, N, 1, C, S, S, block, g["logits_sha"])
+    rng = np.random.Generator(np.random.Philox(key=[int(seed), 911]))
+    coarse = rng.standard_normal(size=(N, 2, -(-S // 8), -(-S // 8)), dtype=np.float32) * np.float32(2.0)
+    unet = (np.repeat(np.repeat(coarse, 8, axis=2), 8, axis=3)[:, :, :S, :S]
+            + rng.standard_normal(size=(N, 2, S, S), dtype=np.float32)).astype(np.float32)
+    assert G.sha(unet) == str(g["unet_sha"])
+    pool = fakes.Pool(logits, labels)
+
+    class PairModel(torch.nn.Module):
+        def __init__(self, pair):
+            super().__init__()
+            self.pair = pair
+
+        @property
+        def module(self):
+            return self
+
+        def forward(self, x):
+            gs = [int(round(float(v) / fakes.GID_SCALE)) for v in x[:, 0, 0, 0].cpu()]
+            seg = torch.from_numpy(np.stack([logits[i, 0] for i in gs])).cuda()
+            return (seg, torch.from_numpy(np.stack([unet[i] for i in gs])).cuda()) if self.pair else seg
+
+    sel = _factory("accuracy_labels", C, pool, S, bs)
+    from deep_active_semantic_segmentation_b200.active_selection import ActiveSelectionAccuracy
+    assert isinstance(sel, ActiveSelectionAccuracy) and isinstance(_factory("accuracy_eval", C, pool, S, bs), ActiveSelectionAccuracy)
+    calls = (("labels", lambda: sel.get_least_accurate_sample_using_labels(PairModel(False), _paths(N), k)),
+             ("softmax", lambda: sel.get_least_accurate_samples(PairModel(True), _paths(N), k, mode='softmax')),
+             ("argmax", lambda: sel.get_least_accurate_samples(PairModel(True), _paths(N), k, mode='argmax')),
+             ("unsure", lambda: sel.get_unsure_samples(PairModel(True), _paths(N), k)))
+    for key, call in calls:
+        chosen = call()
+        assert isinstance(chosen, tuple) and _idx(chosen) == g[key + "_selected"].tolist(), key
+        np.testing.assert_allclose(sel.last_scores, g[key + "_scores"], rtol=RTOL, atol=1e-6, err_msg=key)
+    regions, count = sel.get_least_accurate_region_maps(PairModel(True), _paths(N), G.regions_from_rows(g["existing"], N), Rg, 1)
+    assert count == int(g["count"])
+    assert regions == {str(i): lst for i, lst in enumerate(G.regions_from_rows(g["regions"], N)) if lst}
+    with pytest.raises(NotImplementedError):
+        sel.get_least_accurate_samples(PairModel(True), _paths(N), k, mode='other')
+    # no valid pixel at all -> the 'unsure' mean is NaN like torch's mean of an empty selection
+    from deep_active_semantic_segmentation_b200 import ops
+    sc = ops.accuracy_scores(torch.from_numpy(unet[:1]).cuda(), torch.full((1, S, S), 255.0).cuda(), C)
+    assert np.isnan(sc[0, 3].item()) and sc[0, 4].item() == 0 and sc[0, 1].item() == 0
+
+
+def test_maxsubset_selector_matches_reference():
+    from deep_active_semantic_segmentation_b200.active_selection import get_max_subset_active_selector
+    from tests.test_oracle_vs_golden import _maxsubset_inputs
+    from oracle import restate as R
+    g = G.load("maxsubset")
+    sel = get_max_subset_active_selector(None, None, None)
+    np.random.seed(seed=int(g["ref_seed"]))
+    images = np.concatenate((np.random.normal(loc=2.0, scale=1.0, size=(400, 1024)),
+                             np.random.normal(loc=4.0, scale=1.0, size=(400, 1024)),
+                             np.random.normal(loc=6.0, scale=1.0, size=(150, 1024)),
+                             np.random.normal(loc=4.0, scale=3.0, size=(50, 1024))), axis=0)
+    cand = g["ref_candidates"].tolist()
+    # the reference's own seeded fixture, float64 lists of vectors exactly as tests.py:645 passes them
+    assert sel._max_representative_samples(list(images), list(images[cand, :]), 4) == g["ref_picks"].tolist()
+    for tag in ("a", "b"):
+        X, Y, k = _maxsubset_inputs(g, tag)
+        assert sel._max_representative_samples(list(X), list(Y), k) == g[f"{tag}_picks"].tolist()
+    # more picks than candidates: the reference appends None once everything is taken
+    out = sel._max_representative_samples(images[:50], images[[3, 7, 7]], 4)
+    assert out[:3] == R.max_representative_samples(images[:50], images[[3, 7, 7]], 3) and out[3] is None
+
+
+def test_maxsubset_region_scale_properties():
+    """Region-scale pool (N = 20000 cells, M = 1500 candidates, k = 750): greedy invariants that do not need the
+    O(k M N) host loop - picks are distinct, and the objective after each pick is the minimum over all candidates."""
+    from deep_active_semantic_segmentation_b200 import ops, synth
+    X = torch.from_numpy(synth.coreset_features(3, 20000, 64)).cuda()
+    rng = np.random.default_rng(0)
+    Y = X[torch.from_numpy(rng.integers(0, 20000, 1500)).cuda()] + 0.01
+    picks = ops.maxsubset_greedy(X, Y, 750).cpu().tolist()
+    assert len(set(picks)) == 750 and min(picks) >= 0
+    D = torch.cdist(X.double(), Y.double())                          # [N, M]
+    md = torch.full((20000,), float("inf"), dtype=torch.float64, device="cuda")
+    for step, p in enumerate(picks[:40]):
+        scores = torch.minimum(md[:, None], D).sum(0)
+        scores[picks[:step]] = float("inf")
+        best = float(scores.min())
+        assert abs(float(scores[p]) - best) <= 1e-9 * abs(best)
+        md = torch.minimum(md, D[:, p])

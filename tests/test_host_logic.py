@@ -125,6 +125,24 @@ lo, hi = dist.shard_bounds(5, W, rank)
 local = [R.nms_sequence_single(m[i].copy(), 3, 12) for i in range(lo, hi)]
 seqs = [s for part in dist.gather_objects(local) for s in part]
 assert dist.merge_nms_sequences(seqs, 3, 11.5, 12, 14) == want
+# the same selection through the flattened candidate table (what the device path does: local top-k over
+# (score, flat pool index) pairs -> all-gather of the heads -> lexsort -> stop rule)
+H2, W2, kmax, K = 12, 14, 12, 11.5
+cand_s = np.full((hi - lo, kmax), -np.inf, np.float32)
+cand_f = np.full((hi - lo, kmax), -1, np.int64)
+for a, seq in enumerate(local):
+    for j, (sc, r, c) in enumerate(seq):
+        cand_s[a, j], cand_f[a, j] = sc, ((lo + a) * H2 + r) * W2 + c
+order = np.lexsort((np.arange(cand_s.size), -cand_s.reshape(-1)))[:12]          # stable: ties keep table order
+gs, gi = dist.gather_ranked_np(torch.tensor(cand_s.reshape(-1)[order]), torch.tensor(cand_f.reshape(-1)[order]), 12, True)
+ok = (gi >= 0) & np.isfinite(gs)
+ok[1:] &= gs[1:] >= np.float32(0.01)
+count = int(len(ok) if ok.all() else np.argmin(ok))
+regions = [[] for _ in range(5)]
+for fid in gi[:count].tolist():
+    img, rem = divmod(fid, H2 * W2)
+    regions[img].append((rem // W2, rem % W2, 3, 3))
+assert (regions, count) == want, (regions, count, want)
 td.barrier()
 print("RANK_OK", rank)
 '''

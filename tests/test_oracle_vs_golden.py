@@ -197,3 +197,58 @@ def test_cpu_port_matches_restatement():
         want = R.image_scores(R.mc_maps(logits[b], labels[b], C))
         for k in got:
             np.testing.assert_allclose(got[k][b].item(), want[k], rtol=RTOL, atol=1e-6, err_msg=k)
+
+
+def _unet_head(seed, N, S):
+    rng = np.random.Generator(np.random.Philox(key=[int(seed), 911]))
+    coarse = rng.standard_normal(size=(N, 2, -(-S // 8), -(-S // 8)), dtype=np.float32) * np.float32(2.0)
+    up = np.repeat(np.repeat(coarse, 8, axis=2), 8, axis=3)[:, :, :S, :S]
+    return (up + rng.standard_normal(size=(N, 2, S, S), dtype=np.float32)).astype(np.float32)
+
+
+def test_accuracy_selectors_match_reference():
+    """oracle accuracy_scores / accuracy_error_map vs what the reference's ActiveSelectionAccuracy ranked."""
+    g = G.load("accuracy_small")
+    seed, N, C, S, block, Rg, k, bs = (int(v) for v in g["meta"])
+    logits, labels = G.pool_from_meta(seed, N, 1, C, S, S, block, g["logits_sha"])
+    unet = _unet_head(seed, N, S)
+    assert G.sha(unet) == str(g["unet_sha"])
+    sc = [R.accuracy_scores(logits[i, 0], unet[i], labels[i], C) for i in range(N)]
+    for key, col in (("labels", "wrong_count"), ("softmax", "p0_sum"), ("argmax", "not_argmax_sum"), ("unsure", "unsure_mean")):
+        mine = np.array([s[col] for s in sc], dtype=np.float32)
+        np.testing.assert_allclose(mine, g[key + "_scores"], rtol=1e-5, atol=1e-6, err_msg=key)
+        assert R.rank_topk(g[key + "_scores"].tolist(), k, True) == g[key + "_selected"].tolist()
+    maps = np.stack([R.accuracy_error_map(unet[i], labels[i], C) for i in range(N)])
+    existing = G.regions_from_rows(g["existing"], N)
+    (regions, count), _ = R.region_selection(maps, existing, Rg, 1, S)
+    assert count == int(g["count"])
+    assert regions == G.regions_from_rows(g["regions"], N)
+
+
+def test_maxsubset_matches_reference():
+    """oracle max_representative_samples vs the reference class on its own seeded fixture (tests.py:616-645) and on
+    two float32 pools with duplicated candidates."""
+    g = G.load("maxsubset")
+    np.random.seed(seed=int(g["ref_seed"]))
+    images = np.concatenate((np.random.normal(loc=2.0, scale=1.0, size=(400, 1024)),
+                             np.random.normal(loc=4.0, scale=1.0, size=(400, 1024)),
+                             np.random.normal(loc=6.0, scale=1.0, size=(150, 1024)),
+                             np.random.normal(loc=4.0, scale=3.0, size=(50, 1024))), axis=0)
+    assert G.sha(images) == str(g["ref_images_sha"])
+    cand = g["ref_candidates"].tolist()
+    assert R.max_representative_samples(images, images[cand, :], 4) == g["ref_picks"].tolist()
+    for tag in ("a", "b"):
+        X, Y, k = _maxsubset_inputs(g, tag)
+        assert R.max_representative_samples(X, Y, k) == g[f"{tag}_picks"].tolist()
+
+
+def _maxsubset_inputs(g, tag):
+    from deep_active_semantic_segmentation_b200 import synth
+    seed, N, M, D, k = (int(v) for v in g[f"{tag}_meta"])
+    X = synth.coreset_features(seed, N, D)
+    rng = np.random.default_rng(seed)
+    ci = rng.integers(0, N, size=M)
+    Y = (X[ci] + np.float32(0.05) * rng.standard_normal((M, D)).astype(np.float32)).astype(np.float32)
+    Y[M // 3] = Y[M // 5]
+    assert G.sha(X) == str(g[f"{tag}_x_sha"]) and G.sha(Y) == str(g[f"{tag}_y_sha"])
+    return X, Y, k
