@@ -225,6 +225,7 @@ def run_b200(args):
     alg_bytes = sum(k_bytes) / len(k_bytes)
     peaks, peak_kind = measured_peaks()
     achieved = sum(k_bytes) / (sum(k_ms) * 1e-3) / 1e9
+    tma = G >= T and os.environ.get("DAS_MC_TMA", "1")[:1] != "0"
     traffic = None
     tf = os.path.join(ROOT, "profiles", "k1_traffic.json")
     if os.path.exists(tf):
@@ -234,7 +235,6 @@ def run_b200(args):
                 traffic = tj.get("dram_bytes_per_launch")
         except Exception:
             traffic = None
-    tma = G >= T and os.environ.get("DAS_MC_TMA", "1")[:1] != "0"
     kname = ("mc_score_tma_kernel<C=19> (fused K1+K2, TMA ring, persistent)" if tma else
              "mc_score_kernel<C=19,VEC=2> (fused K1+K2, LDG)" if G >= T else
              "mc_accumulate_kernel / mc_score_kernel <C=19,VEC=2>")

@@ -137,12 +137,12 @@ __global__ void __launch_bounds__(kTmaThreads, tma_ctas_per_sm(C)) mc_score_tma_
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const int b = tile / q.tiles_per_image, blk = tile % q.tiles_per_image;
         // pixel p[j] of this thread inside the plane, act[j]: it exists
-        long long p[VEC];
+        int p[VEC];  // < H*W < 2^30 (mc_validate)
         bool act[VEC];
 #pragma unroll
         for (int j = 0; j < VEC; ++j) {
-            p[j] = (long long)blk * TILE + (FLAT ? tid + j * HALF : tid * VEC + j);
-            act[j] = p[j] < q.HW && (!FLAT || tid < HALF);
+            p[j] = blk * TILE + (FLAT ? tid + j * HALF : tid * VEC + j);
+            act[j] = p[j] < (int)hw && (!FLAT || tid < HALF);
         }
         const uint32_t e0 = FLAT ? (uint32_t)b * C * hw + (uint32_t)blk * TILE : 0u;
         if (VOTES) {
