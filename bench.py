@@ -25,6 +25,10 @@ import sys
 import threading
 import time
 
+# NCCL prints its version banner on stdout when NCCL_DEBUG is VERSION: keep stdout to the one JSON line
+if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+    os.environ["NCCL_DEBUG"] = "WARN"
+
 ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
@@ -124,7 +128,19 @@ def init_dist(n_gpus: int):
         import torch.distributed as td
         torch.cuda.set_device(local)
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        td.init_process_group("nccl", device_id=torch.device("cuda", local))
+        # NCCL writes its version banner to stdout when the first communicator is created; stdout must carry
+        # exactly one JSON line, so the banner is sent to stderr (fd level: it comes from C code)
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            td.init_process_group("nccl", device_id=torch.device("cuda", local))
+            td.all_reduce(torch.zeros(1, device="cuda"))
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
     else:
         torch.cuda.set_device(0)
     return world, rank, local

@@ -132,13 +132,23 @@ class ActiveSelectionBase:
 
 def region_tail(selector, score_maps, images, lo, region_size, selection_size):
     """Everything after the per-image box sums of create_region_maps (mc_dropout.py:152-171):
-    pool min-max normalisation, image-local NMS sequences on the GPU, global merge, result dict."""
-    N_local, H2, W2 = score_maps.shape
+    pool min-max normalisation, image-local NMS sequences on the GPU, global order, result dict.
+    score_maps is None on a rank whose shard of the pool is empty (more ranks than images): it still takes part
+    in every exchange, with neutral contributions."""
+    dims = None if score_maps is None else (int(score_maps.shape[1]), int(score_maps.shape[2]))
+    known = [d for d in dist.gather_objects(dims) if d is not None]
+    if not known:
+        raise IndexError("list index out of range")      # empty pool: the reference fails on zip(*[])
+    H2, W2 = known[0]
     H, W = H2 + region_size - 1, W2 + region_size - 1
     base_sq = H * W   # == base_size**2 for the reference's square crops (mc_dropout.py:129,157)
     num_requested = (selection_size * base_sq) / (region_size * region_size)
-    mm = dist.allreduce_minmax(selector._minmax)
-    ops.minmax_normalise(score_maps, mm)
+    local_mm = selector._minmax if score_maps is not None else ops.new_minmax(torch.device("cuda", torch.cuda.current_device()))
+    mm = dist.allreduce_minmax(local_mm)
+    if score_maps is None:
+        score_maps = torch.empty((0, H2, W2), dtype=torch.float32, device=mm.device)
+    else:
+        ops.minmax_normalise(score_maps, mm)
     kmax = max(1, min(math.ceil(num_requested), ops.nms_pick_bound(H2, W2, region_size)))
     regions, count = global_nms(score_maps, lo, len(images), region_size, num_requested, kmax)
     new_regions = {images[i]: regions[i] for i in range(len(regions)) if regions[i]}
@@ -158,13 +168,20 @@ def global_nms(score_maps, lo, n_images, region_size, max_selection_count, kmax)
     N_local, H2, W2 = score_maps.shape
     want = math.ceil(max_selection_count)
     if want > TOPK_MAX_K:       # more picks than one K3 launch ranks: k-way merge of the sequences on the host
-        cs, rc, cnt = ops.nms_sequences(score_maps, region_size, kmax, 0.01)
+        local = []
+        if N_local > 0:
+            cs, rc, cnt = ops.nms_sequences(score_maps, region_size, kmax, 0.01)
+            local = dist.sequences_from_device(cs, rc, cnt)
         seqs = []
-        for part in dist.gather_objects(dist.sequences_from_device(cs, rc, cnt)):
+        for part in dist.gather_objects(local):
             seqs += part
         return dist.merge_nms_sequences(seqs, region_size, max_selection_count, H2, W2)
-    cs, rc, cnt, flat = ops.nms_sequences(score_maps, region_size, kmax, 0.01, image_offset=lo, with_flat=True)
-    s, ids = ops.topk(cs.reshape(-1), min(want, cs.numel()), True, ids=flat.reshape(-1))
+    if N_local > 0:
+        cs, rc, cnt, flat = ops.nms_sequences(score_maps, region_size, kmax, 0.01, image_offset=lo, with_flat=True)
+        s, ids = ops.topk(cs.reshape(-1), min(want, cs.numel()), True, ids=flat.reshape(-1))
+    else:
+        s = torch.empty(0, dtype=torch.float32, device=score_maps.device)
+        ids = torch.empty(0, dtype=torch.int64, device=score_maps.device)
     gs, gi = dist.gather_ranked_np(s, ids, max(want, 1), True)
     # stop rule on the merged prefix: candidates exist (id >= 0, score > -inf), at most `want` picks, and every
     # pick after the first needs score >= 0.01 (the pool maximum the reference checks after the previous pick)

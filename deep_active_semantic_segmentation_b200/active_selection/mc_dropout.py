@@ -81,8 +81,6 @@ class ActiveSelectionMCDropout(ActiveSelectionBase):
             ops.suppress_rects(maps, rects)
             ops.box_sum(maps, region_size, self._minmax, out=score_maps[ctr:ctr + B])
             ctr += B
-        if score_maps is None:
-            raise base.DasError("this rank received an empty shard of the pool; use fewer ranks than images")
         return base.region_tail(self, score_maps, images, lo, region_size, selection_size)
 
     def create_region_maps(self, model, images, existing_regions, region_size, selection_size):

@@ -23,7 +23,7 @@ def main():
     torch.cuda.set_device(local)
     os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
     td.init_process_group("nccl", device_id=torch.device("cuda", local))
-    from deep_active_semantic_segmentation_b200 import constants, synth
+    from deep_active_semantic_segmentation_b200 import constants, dist, synth
     from deep_active_semantic_segmentation_b200.active_selection import base, get_active_selection_class
 
     base.paths_dataset.PathsDataset = fakes.SyntheticPathsDataset
@@ -60,6 +60,20 @@ def main():
         assert count == int(g["count"]), (rank, name, count)
         assert regions == {str(i): lst for i, lst in enumerate(G.regions_from_rows(g["regions"], N)) if lst}
         done.append(name)
+
+    # fewer images than ranks: ranks with an empty shard must still take part in every exchange
+    g = G.load("region_small")
+    seed, N, T, C, S, block, Rg, sel_size, bs = (int(v) for v in g["meta"])
+    logits, labels = G.pool_from_meta(seed, N, T, C, S, S, block, g["logits_sha"])
+    pool = fakes.Pool(logits[:1], labels[:1])
+    constants.MC_STEPS = T
+    sel = get_active_selection_class("variance", C, pool, S, bs)
+    one = sel.create_region_maps(fakes.ReplayModel(pool), paths(1), [[]], Rg, sel_size)
+    chosen = sel.get_vote_entropy_for_images(fakes.ReplayModel(pool), paths(1), 3)
+    assert chosen == ("0",) and one[1] >= 1 and set(one[0]) == {"0"}, (rank, one, chosen)
+    gathered = dist.gather_objects(one)
+    assert all(x == gathered[0] for x in gathered)
+    done.append("one-image pool")
 
     for name, force in (("coreset_small", True), ("coreset_mid", True), ("coreset_mid", False)):
         g = G.load(name)
