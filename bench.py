@@ -262,8 +262,10 @@ def run_b200(args):
 
     e2e = None if args.no_e2e else run_e2e(args, world, rank, dev)
     cpu = None
+    torch_gpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu = cpu_baseline([p[:1].cpu() for p in passes], labels[:1].cpu(), budget_s=20.0)
+        torch_gpu = torch_gpu_baseline(passes, labels)
 
     if rank == 0:
         line = {
@@ -276,7 +278,7 @@ def run_b200(args):
                                   "probs": "pred_entropy+bald+confidence+margin"}[args.mode],
                        "sharding": f"by image, {world} rank(s), candidate all-gather only",
                        "l2": f"inputs {T * B * C * H * W * 4 / 1e9:.2f} GB per step >> 126 MB L2 (no flush needed)"},
-            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+            "roofline": roofline, "cpu_baseline": cpu, "torch_gpu_baseline": torch_gpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
             "selected_head": [int(v) for v in (chosen[:5].tolist() if hasattr(chosen, "tolist") else chosen[:5])],
         }
         print(json.dumps(line), flush=True)
@@ -410,6 +412,27 @@ def cpu_baseline(pass_logits_1img, labels_1img, budget_s: float):
     dt = time.perf_counter() - t0
     return {"value": round(n / dt, 4), "unit": UNIT, "cores": cores, "kind": "port",
             "sample": f"{n} image(s) of {H}x{W}, C={C}, T={T} (after 1 untimed), oracle/cpu_port.py (torch CPU ops in the reference's order)"}
+
+
+def torch_gpu_baseline(passes, labels):
+    """The reference's op sequence (oracle/cpu_port.py, same ATen ops in the same order) run by PyTorch eager on the
+    SAME B200, inputs resident in HBM: the "same-box PyTorch" comparator of SURVEY.md section 8(d).  Reported only."""
+    import torch
+    from oracle import cpu_port
+
+    B = passes[0].shape[0]
+    cpu_port.score_batch(passes, labels, C)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    n = 3
+    e0.record()
+    for _ in range(n):
+        cpu_port.score_batch(passes, labels, C)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / n
+    return {"value": round(B / (ms * 1e-3), 2), "unit": UNIT, "ms_per_batch": round(ms, 3), "batch_images": B,
+            "kind": "reference op sequence in PyTorch eager on this GPU (oracle/cpu_port.py with CUDA tensors)"}
 
 
 def run_reference(args):

@@ -16,23 +16,25 @@ import torch
 
 
 def score_batch(pass_logits, labels, C: int, want_probs: bool = True):
-    """pass_logits: list of T float32 CPU tensors [B,C,H,W]; labels [B,H,W] float32.
+    """pass_logits: list of T float32 tensors [B,C,H,W] (CPU for the CPU baseline; CUDA tensors give the
+    "same-box PyTorch eager" comparator); labels [B,H,W] float32.
     -> dict of float32 [B] image scores (vote_entropy, and with want_probs pred_entropy / bald /
     expected_entropy / confidence / margin)."""
     T = len(pass_logits)
     B, _, H, W = pass_logits[0].shape
-    outputs = torch.empty(B, T, H, W, dtype=torch.float32)
+    dev = pass_logits[0].device
+    outputs = torch.empty(B, T, H, W, dtype=torch.float32, device=dev)
     softmax = torch.nn.Softmax2d()
     if want_probs:
-        p_sum = torch.zeros(B, C, H, W, dtype=torch.float32)
-        e_sum = torch.zeros(B, H, W, dtype=torch.float32)
+        p_sum = torch.zeros(B, C, H, W, dtype=torch.float32, device=dev)
+        e_sum = torch.zeros(B, H, W, dtype=torch.float32, device=dev)
     with torch.no_grad():
         for t, x in enumerate(pass_logits):
             outputs[:, t] = torch.argmax(x, dim=1)
             if want_probs:
                 p = softmax(x)
                 p_sum += p
-                e = torch.zeros(B, H, W, dtype=torch.float32)
+                e = torch.zeros(B, H, W, dtype=torch.float32, device=dev)
                 for c in range(C):
                     e = e - p[:, c] * torch.log2(p[:, c] + 1e-12)
                 e_sum += e
@@ -40,7 +42,7 @@ def score_batch(pass_logits, labels, C: int, want_probs: bool = True):
                                if want_probs else ("vote_entropy",))}
         for i in range(B):
             mask = (labels[i] < 0) | (labels[i] >= C)
-            ve = torch.zeros(H, W, dtype=torch.float32)
+            ve = torch.zeros(H, W, dtype=torch.float32, device=dev)
             for c in range(C):
                 p = torch.sum(outputs[i] == c, dim=0, dtype=torch.float32) / T
                 ve = ve - p * torch.log2(p + 1e-12)
@@ -48,7 +50,7 @@ def score_batch(pass_logits, labels, C: int, want_probs: bool = True):
             res["vote_entropy"].append(torch.mean(ve))
             if want_probs:
                 pb = p_sum[i] / T
-                pe = torch.zeros(H, W, dtype=torch.float32)
+                pe = torch.zeros(H, W, dtype=torch.float32, device=dev)
                 for c in range(C):
                     pe = pe - pb[c] * torch.log2(pb[c] + 1e-12)
                 ee = e_sum[i] / T

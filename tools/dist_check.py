@@ -75,16 +75,18 @@ def main():
     assert all(x == gathered[0] for x in gathered)
     done.append("one-image pool")
 
-    for name, force in (("coreset_small", True), ("coreset_mid", True), ("coreset_mid", False)):
+    for name, force, shard in (("coreset_small", True, True), ("coreset_mid", True, True), ("coreset_mid", False, True),
+                               ("coreset_mid", "auto", "auto")):
         g = G.load(name)
         seed, N, D, L, K = (int(v) for v in g["meta"])
         feats = synth.coreset_features(seed, N, D)
         sel = get_active_selection_class("coreset", 2, None, None, 4)
-        sel.tensor_core_filter = force           # rows of min_d sharded, per-rank tcgen05 filter on / off
+        sel.tensor_core_filter = force           # per-rank tcgen05 filter on / off
+        sel.shard_rows = shard                   # rows of min_d sharded (one exchange per step) / replicated loop
         picks = sel._select_batch(feats.astype(np.float64), list(range(L)), K)
         assert picks == g["picks"].tolist(), (rank, name)
         np.testing.assert_allclose(sel.last_min_distances.cpu().numpy(), g["min_dist"], rtol=1e-9, atol=1e-4)
-        done.append(f"{name}/filter={force}")
+        done.append(f"{name}/filter={force}/shard={shard}")
 
     td.barrier()
     if rank == 0:
