@@ -583,9 +583,14 @@ static bool kc_cluster_enabled() {
 
 // scratch table for the step-wise (multi-GPU) entry points: one per process is enough because the
 // ABI is thread-compatible, not thread-safe.
-static KcBest* g_step_table = nullptr;
+static KcBest* g_step_tables[64] = {nullptr};  // one per device ordinal
+static KcBest* g_step_table = nullptr;         // the current device's table (set by ensure_step_table)
 static int ensure_step_table() {
-    if (g_step_table == nullptr) DAS_CUDA(cudaMalloc(&g_step_table, (size_t)kNumSMs * 4 * sizeof(KcBest)));
+    int dev = 0;
+    DAS_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64) return DAS_ERR_UNSUPPORTED;
+    if (g_step_tables[dev] == nullptr) DAS_CUDA(cudaMalloc(&g_step_tables[dev], (size_t)kNumSMs * 4 * sizeof(KcBest)));
+    g_step_table = g_step_tables[dev];
     return DAS_OK;
 }
 

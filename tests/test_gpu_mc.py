@@ -243,3 +243,26 @@ def test_tma_ring_kernel_is_bit_identical_to_ldg_kernel(B, T, C, H, W, probs, vo
 def _lib_launches():
     from deep_active_semantic_segmentation_b200 import _lib
     return _lib.launch_count()
+
+
+@pytest.mark.parametrize("H,W,C,T", [(512, 1024, 19, 20), (513, 513, 21, 20)])
+def test_tma_vs_ldg_bitwise_at_baseline_size(H, W, C, T, monkeypatch):
+    """BASELINE shapes (Cityscapes 512x1024 C=19, Pascal 513x513 C=21; T=20), inputs generated on the device:
+    the TMA ring kernel (3-D maps / flat shifted 1-D maps) and the LDG kernel must produce bit-identical maps."""
+    ops = _ops()
+    B = 2
+    passes, labels = synth.device_pass_logits(77, 0, B, T, C, H, W, torch.device("cuda", 0))
+    maps = list(ops.MAP_NAMES)
+    outs = {}
+    for tma in ("1", "0"):
+        monkeypatch.setenv("DAS_MC_TMA", tma)
+        st = ops.MCState(B, C, H, W, T, votes=True, probs=True, single_shot=True)
+        outs[tma] = st.score(passes, labels, maps=maps, scores=True, weak_labels=True)
+        torch.cuda.synchronize()
+    for k in maps + ["weak_labels"]:
+        assert torch.equal(outs["1"][k], outs["0"][k]), k
+    np.testing.assert_allclose(outs["1"]["scores"].cpu().numpy(), outs["0"]["scores"].cpu().numpy(), rtol=2e-6, atol=1e-7)
+    # sanity of the content: masked border is exactly 0 / 1, BALD >= -eps, unanimous pixels have zero vote entropy
+    ve, bald, conf = outs["1"]["vote_entropy"], outs["1"]["bald"], outs["1"]["confidence"]
+    assert float(ve[:, :16].abs().max()) == 0.0 and float(conf[:, :16].min()) == 1.0
+    assert float(bald.min()) > -1e-5 and float(ve.max()) <= np.log2(min(C, T)) + 1e-5
