@@ -63,6 +63,13 @@ __device__ __forceinline__ float ex2_approx(float x) {
     return y;
 }
 
+// MUFU.RCP alone (relative error <= 2^-23); used where the argument is known to be a normal number
+__device__ __forceinline__ float rcp_approx(float x) {
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
 // Blackwell packed fp32: one FFMA2 / FADD2 / FMUL2 issue slot does two IEEE fp32 operations (lane-wise, same
 // rounding as the scalar instructions).  The kernels that own pixel PAIRS use them to halve the issue
 // slots of the softmax arithmetic.

@@ -199,8 +199,8 @@ __device__ __forceinline__ uint32_t mc_pass_math(float (&x)[C][VEC], Acc<C, VEC,
                     x[c][j0] = e.x;
                     x[c][j1] = e.y;
                 }
-                inv[j0] = __frcp_rn(s.x);
-                inv[j1] = __frcp_rn(s.y);
+                inv[j0] = rcp_approx(s.x);  // s in [1, C]: 1 ulp, no denormal slow path
+                inv[j1] = rcp_approx(s.y);
                 ent[j0] += log2f(s.x) - a.x * inv[j0];
                 ent[j1] += log2f(s.y) - a.y * inv[j1];
             }
@@ -230,7 +230,7 @@ __device__ __forceinline__ uint32_t mc_pass_math(float (&x)[C][VEC], Acc<C, VEC,
                     a = fmaf(e, y, a);
                     x[c][j] = e;
                 }
-                inv[j] = __frcp_rn(s);
+                inv[j] = rcp_approx(s);
                 ent[j] += log2f(s) - a * inv[j];
             }
 #pragma unroll
