@@ -459,7 +459,8 @@ def run_reference(args):
     cpu_port.score_batch(passes, lab, C)
     per_row = (time.perf_counter() - t0) / 32
     rows = H
-    while rows > 16 and per_row * rows * (K + Wm) > 120.0:
+    budget_s = float(os.environ.get("DAS_REF_BUDGET_S", 120.0))     # whole --impl reference run, seconds
+    while rows > 16 and per_row * rows * (K + Wm) > budget_s:
         rows //= 2
     passes, lab = make(rows)
     for _ in range(Wm):

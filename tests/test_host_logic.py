@@ -157,3 +157,21 @@ def test_gloo_world_size_2_exchanges(tmp_path):
     outs = [p.communicate(timeout=180)[0] for p in procs]
     for r, (p, out) in enumerate(zip(procs, outs)):
         assert p.returncode == 0 and f"RANK_OK {r}" in out, out
+
+
+def test_bench_reference_arm_prints_one_json_line():
+    """`bench.py --impl reference` (the CPU arm the driver runs beside ours) needs no GPU: one JSON line with the
+    contract keys, same metric / unit / workload as the B200 arm."""
+    import json
+    env = dict(os.environ, DAS_REF_BUDGET_S="4")
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "2", "--warmup", "1"],
+                         capture_output=True, text=True, timeout=600, env=env)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["unit"] == "images/s" and d["higher_is_better"] is True
+    assert d["metric"].startswith("pool images scored/sec") and d["value"] > 0 and d["steps"] == 2
+    assert d["config"]["workload"] == "mc_dropout_entropy_bald_cityscapes_pool_512x1024_c19_t20"
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"] == {"value": d["value"], "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
