@@ -3,7 +3,7 @@
  *
  * This is the drop-in boundary for the scoring hot path of
  * nihalsid/deep-active-semantic-segmentation.  The reference has no FFI layer of its own: its
- * boundary is the Python method surface of active_selection/*.py.  The Python mirror of that
+ * boundary is the Python method surface of active_selection (all .py files).  The mirror of that
  * surface lives in deep_active_semantic_segmentation_b200/active_selection/ and calls ONLY
  * the functions declared here (via ctypes; see INTEGRATION.md for the binding stub).  Each entry
  * point cites the reference code whose body it replaces (paths relative to the reference tree).

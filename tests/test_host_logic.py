@@ -175,3 +175,14 @@ def test_bench_reference_arm_prints_one_json_line():
     assert d["config"]["workload"] == "mc_dropout_entropy_bald_cityscapes_pool_512x1024_c19_t20"
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"] == {"value": d["value"], "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+
+
+def test_header_is_plain_c(tmp_path):
+    """include/das_b200.h is the C ABI: it must compile as C99 with no torch / C++ types in any signature."""
+    src = tmp_path / "h.c"
+    src.write_text('#include "das_b200.h"\nint main(void) { return DAS_ABI_VERSION + DAS_N_SCORES + DAS_ACC_N; }\n')
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(ROOT, "include"),
+                        "-fsyntax-only", str(src)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    header = open(os.path.join(ROOT, "include", "das_b200.h")).read()
+    assert "torch" not in header.replace("no torch", "") and "std::" not in header and "at::" not in header
