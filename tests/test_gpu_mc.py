@@ -266,3 +266,25 @@ def test_tma_vs_ldg_bitwise_at_baseline_size(H, W, C, T, monkeypatch):
     ve, bald, conf = outs["1"]["vote_entropy"], outs["1"]["bald"], outs["1"]["confidence"]
     assert float(ve[:, :16].abs().max()) == 0.0 and float(conf[:, :16].min()) == 1.0
     assert float(bald.min()) > -1e-5 and float(ve.max()) <= np.log2(min(C, T)) + 1e-5
+
+
+@pytest.mark.parametrize("C", [2, 3, 5, 8, 13, 16, 20, 22, 24, 25, 28, 31, 32])
+def test_every_class_count_family_tma_ldg_oracle(C, monkeypatch):
+    """One representative per register / shared-memory configuration of the kernels (C <= 20, 21-24, 25-32; LDG
+    accumulators in registers vs shared memory): TMA == LDG bit for bit, both == oracle, on an aligned and an odd plane."""
+    ops = _ops()
+    for (H, W) in ((16, 32), (23, 29)):
+        B, T = 2, 4
+        logits = synth.pool_logits(100 + C, [0, 1], T, C, H, W, 8)
+        labels = synth.pool_labels(100 + C, [0, 1], H, W, C, 8)
+        dev = [torch.from_numpy(np.ascontiguousarray(logits[:, t])).cuda() for t in range(T)]
+        lab = torch.from_numpy(labels).cuda()
+        outs = {}
+        for tma in ("1", "0"):
+            monkeypatch.setenv("DAS_MC_TMA", tma)
+            st = ops.MCState(B, C, H, W, T, votes=True, probs=True, single_shot=True)
+            outs[tma] = st.score(dev, lab, maps=list(ops.MAP_NAMES), scores=True)
+            torch.cuda.synchronize()
+        for k in ops.MAP_NAMES:
+            assert torch.equal(outs["1"][k], outs["0"][k]), (C, H, W, k)
+        check_against_oracle({k: v.cpu().numpy() for k, v in outs["1"].items()}, logits, labels)
