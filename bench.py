@@ -328,7 +328,7 @@ def run_e2e(args, world, rank, dev):
     base.paths_dataset.PathsDataset, constants.MC_STEPS = HostDataset, T
     try:
         sel = ActiveSelectionMCDropout(C, None, -1, B)
-        sel.pass_group = 1          # streaming: a pass is scored as soon as its copy has landed
+        # default pass grouping: the T copies of a batch are enqueued back to back, then ONE fused launch scores them
         model = HostReplayModel().to(dev)
         images = [str(i) for i in range(world * K * B)]
         sel.get_mc_scores_for_images(model, images[: world * B], TOPK)      # warm-up
