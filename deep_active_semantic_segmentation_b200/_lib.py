@@ -11,7 +11,7 @@ import os
 PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(PKG, "libdas_b200.so")
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 MC_VOTES = 1
 MC_PROBS = 2
 MC_SINGLE_SHOT = 4
@@ -45,6 +45,9 @@ _PROTOTYPES = {
     "das_mc_finalize": (_i, [C.POINTER(McDesc), _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "das_mc_accumulate_finalize": (_i, [C.POINTER(McDesc), _vp, C.POINTER(_vp), _i, _i, _vp, _vp, _vp, _vp, _vp, _vp,
                                          _vp, _vp, _vp]),
+    "das_mc_upsample_accumulate_finalize": (_i, [C.POINTER(McDesc), _vp, C.POINTER(_vp), _i, _i, _i, _vp, _vp, _vp,
+                                                  _vp, _vp, _vp, _vp, _vp, _vp]),
+    "das_mc_upsample_supported": (_i, [_i, _i, _i, _i]),
     "das_mc_votes_ptr": (_i, [C.POINTER(McDesc), _vp, C.POINTER(_vp)]),
     "das_suppress_rects": (_i, [_vp, _i, _i, _i, _vp, _i, _vp]),
     "das_add_maps": (_i, [_vp, _vp, _sz, _vp]),

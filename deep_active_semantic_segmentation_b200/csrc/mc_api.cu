@@ -16,7 +16,8 @@ unsigned long long g_launch_count = 0;
     int dispatch_accumulate_##LO##_##HI(const McAccParams&, int, int, int, cudaStream_t);             \
     int dispatch_finalize_##LO##_##HI(const McFinParams&, int, int, int, cudaStream_t);               \
     int dispatch_score_##LO##_##HI(const McScoreParams&, int, int, int, cudaStream_t);                \
-    int dispatch_score_tma_##LO##_##HI(const McTmaParams&, int, int, cudaStream_t);
+    int dispatch_score_tma_##LO##_##HI(const McTmaParams&, int, int, cudaStream_t);                   \
+    int dispatch_score_up_##LO##_##HI(const McUpParams&, int, int, cudaStream_t);
 DAS_DECL_RANGE(2, 9)
 DAS_DECL_RANGE(10, 16)
 DAS_DECL_RANGE(17, 20)
@@ -59,6 +60,16 @@ int dispatch_score_tma(const McTmaParams& p, int f, int ctas, cudaStream_t st) {
     if (C <= 24) return dispatch_score_tma_21_24(p, f, ctas, st);
     if (C <= 28) return dispatch_score_tma_25_28(p, f, ctas, st);
     return dispatch_score_tma_29_32(p, f, ctas, st);
+}
+
+int dispatch_score_up(const McUpParams& p, int f, int ctas, cudaStream_t st) {
+    const int C = p.fin.C;
+    if (C <= 9) return dispatch_score_up_2_9(p, f, ctas, st);
+    if (C <= 16) return dispatch_score_up_10_16(p, f, ctas, st);
+    if (C <= 20) return dispatch_score_up_17_20(p, f, ctas, st);
+    if (C <= 24) return dispatch_score_up_21_24(p, f, ctas, st);
+    if (C <= 28) return dispatch_score_up_25_28(p, f, ctas, st);
+    return dispatch_score_up_29_32(p, f, ctas, st);
 }
 
 int mc_validate(const das_mc_desc* d) {
@@ -107,7 +118,10 @@ McLayout mc_layout(const das_mc_desc& d) {
     L.partials = off;
     // sized for the finest block partition any kernel uses (the TMA kernel: 256-pixel tiles)
     const int blocks_tma = (int)((HW + kTmaFlatPix - 1) / kTmaFlatPix);
-    const int blocks_max = L.blocks_fused > blocks_tma ? L.blocks_fused : blocks_tma;
+    // ... and the fused-upsample kernel: 16 x 16 tiles
+    const int blocks_up = ((d.H + kUpTile - 1) / kUpTile) * ((d.W + kUpTile - 1) / kUpTile);
+    int blocks_max = L.blocks_fused > blocks_tma ? L.blocks_fused : blocks_tma;
+    if (blocks_up > blocks_max) blocks_max = blocks_up;
     off += align_up((size_t)d.B * blocks_max * DAS_N_SCORES * sizeof(float), 256);
     L.total = off;
     return L;
@@ -262,6 +276,26 @@ static int fill_tma_params(const das_mc_desc* desc, const McScoreParams& q, McTm
     return DAS_OK;
 }
 
+// ---- fused bilinear upsample (low-resolution logits) --------------------------------------------
+static McUpParams g_up_params;
+
+// ATen's align_corners scale (area_pixel_compute_scale<float>)
+static float up_scale(int n_in, int n_out) { return n_out > 1 ? (float)(n_in - 1) / (float)(n_out - 1) : 0.f; }
+// does every 16-pixel tile of the output axis read at most kUpRows consecutive source samples?  (the kernel's
+// arithmetic, replayed on the host: IEEE float multiply, truncation)
+static bool up_window_fits(int n_in, int n_out, float scale) {
+    for (int t0 = 0; t0 < n_out; t0 += kUpTile) {
+        const int last = (t0 + kUpTile - 1 < n_out ? t0 + kUpTile - 1 : n_out - 1);
+        int base = (int)(scale * (float)t0);
+        if (base > n_in - 1) base = n_in - 1;
+        int i0 = (int)(scale * (float)last);
+        if (i0 > n_in - 1) i0 = n_in - 1;
+        const int i1 = i0 + (i0 < n_in - 1 ? 1 : 0);
+        if (i1 - base > kUpRows - 1) return false;
+    }
+    return true;
+}
+
 extern "C" {
 
 const char* das_strerror(int status) {
@@ -350,6 +384,45 @@ int das_mc_accumulate_finalize(const das_mc_desc* desc, void* state, const float
     } else {
         rc = dispatch_score(q, desc->B, acc_vec(*desc), flags, st);
     }
+    if (rc != DAS_OK) return rc;
+    return reduce_partials(desc, q.fin, image_scores, st);
+}
+
+int das_mc_upsample_supported(int h, int w, int H, int W) {
+    if (h < 1 || w < 1 || H < 1 || W < 1) return 0;
+    return up_window_fits(h, H, up_scale(h, H)) && up_window_fits(w, W, up_scale(w, W)) ? 1 : 0;
+}
+
+int das_mc_upsample_accumulate_finalize(const das_mc_desc* desc, void* state, const float* const* pass_lowres_logits,
+                                        int n_passes, int h, int w, const float* labels, float* vote_entropy,
+                                        float* pred_entropy, float* bald, float* confidence, float* margin,
+                                        uint8_t* weak_labels, float* image_scores, void* stream) {
+    int rc = mc_validate(desc);
+    if (rc != DAS_OK) return rc;
+    if (pass_lowres_logits == nullptr || h < 1 || w < 1) return DAS_ERR_INVALID_ARG;
+    if (n_passes < 1 || n_passes > desc->T_cap) return DAS_ERR_INVALID_ARG;
+    if (n_passes > DAS_MAX_PASS_GROUP) return DAS_ERR_UNSUPPORTED;
+    if (!das_mc_upsample_supported(h, w, desc->H, desc->W)) return DAS_ERR_UNSUPPORTED;
+    // source offsets inside one image are formed in 32 bits
+    if ((unsigned long long)desc->C * h * w >= (1ull << 31)) return DAS_ERR_UNSUPPORTED;
+    McUpParams& q = g_up_params;
+    const int tiles_x = (desc->W + kUpTile - 1) / kUpTile, tiles_y = (desc->H + kUpTile - 1) / kUpTile;
+    rc = fill_fin_params(desc, state, labels, n_passes, vote_entropy, pred_entropy, bald, confidence, margin,
+                         weak_labels, tiles_x * tiles_y, &q.fin);
+    if (rc != DAS_OK) return rc;
+    for (int g = 0; g < DAS_MAX_PASS_GROUP; ++g) {
+        q.lowres[g] = g < n_passes ? pass_lowres_logits[g] : nullptr;
+        if (g < n_passes && (q.lowres[g] == nullptr)) return DAS_ERR_INVALID_ARG;
+        if (g < n_passes && misaligned(q.lowres[g], 4)) return DAS_ERR_MISALIGNED;
+    }
+    q.B = desc->B;
+    q.n_passes = n_passes;
+    q.stages = 0;
+    q.h = h, q.w = w, q.H = desc->H, q.W = desc->W;
+    q.tiles_x = tiles_x, q.tiles_y = tiles_y;
+    q.rh = up_scale(h, desc->H), q.rw = up_scale(w, desc->W);
+    cudaStream_t st = (cudaStream_t)stream;
+    rc = dispatch_score_up(q, desc->flags & (DAS_MC_VOTES | DAS_MC_PROBS), tma_ctas_per_sm(), st);
     if (rc != DAS_OK) return rc;
     return reduce_partials(desc, q.fin, image_scores, st);
 }

@@ -164,7 +164,41 @@ int launch_score_tma(const McTmaParams& p, int flags, int ctas_per_sm, cudaStrea
 }
 
 template <int C>
+int launch_score_up(const McUpParams& p, int flags, int ctas_per_sm, cudaStream_t st) {
+    const bool probs = flags & DAS_MC_PROBS, votes = flags & DAS_MC_VOTES;
+    if (ctas_per_sm <= 0) ctas_per_sm = up_ctas_per_sm(C);
+    // ring depth: the windows are small (C * 192 bytes), 4 stages keep one producer round trip ahead of the consumers
+    McUpParams q = p;
+    q.stages = 4;
+    const size_t smem = 2 * up_rows_bytes(C) + (size_t)q.stages * up_stage_bytes(C);
+    const int tiles = p.B * p.tiles_x * p.tiles_y;
+#define DAS_UP(P, Q)                                                                               \
+    do {                                                                                           \
+        int rc__ = set_smem(mc_score_up_kernel<C, P, Q>, smem);                                    \
+        if (rc__ != DAS_OK) return rc__;                                                           \
+        int occ__ = 0;                                                                             \
+        cudaError_t e__ = cudaOccupancyMaxActiveBlocksPerMultiprocessor(                           \
+            &occ__, mc_score_up_kernel<C, P, Q>, kUpThreads, smem);                                \
+        if (e__ != cudaSuccess) return cuda_fail(e__);                                             \
+        if (occ__ < 1) return DAS_ERR_UNSUPPORTED;                                                 \
+        if (occ__ > ctas_per_sm) occ__ = ctas_per_sm;                                              \
+        const int grid__ = tiles < kNumSMs * occ__ ? tiles : kNumSMs * occ__;                      \
+        DAS_LAUNCH((mc_score_up_kernel<C, P, Q>), grid__, kUpThreads, smem, st, q);                \
+    } while (0)
+    if (probs && votes) DAS_UP(true, true);
+    else if (probs) DAS_UP(true, false);
+    else DAS_UP(false, true);
+#undef DAS_UP
+    DAS_CHECK_LAUNCH();
+    return DAS_OK;
+}
+
+template <int C>
 struct Range {
+    static int score_up(const McUpParams& p, int f, int ctas, cudaStream_t st) {
+        if (p.fin.C == C) return launch_score_up<C>(p, f, ctas, st);
+        return Range<C + 1>::score_up(p, f, ctas, st);
+    }
     static int score_tma(const McTmaParams& p, int f, int ctas, cudaStream_t st) {
         if (p.fin.C == C) return launch_score_tma<C>(p, f, ctas, st);
         return Range<C + 1>::score_tma(p, f, ctas, st);
@@ -188,6 +222,7 @@ struct Range<DAS_C_HI + 1> {
     static int fin(const McFinParams&, int, int, int, cudaStream_t) { return DAS_ERR_UNSUPPORTED; }
     static int score(const McScoreParams&, int, int, int, cudaStream_t) { return DAS_ERR_UNSUPPORTED; }
     static int score_tma(const McTmaParams&, int, int, cudaStream_t) { return DAS_ERR_UNSUPPORTED; }
+    static int score_up(const McUpParams&, int, int, cudaStream_t) { return DAS_ERR_UNSUPPORTED; }
 };
 
 #define DAS_CAT_(a, b, c) a##b##_##c
@@ -204,6 +239,9 @@ int DAS_CAT(dispatch_score_, DAS_C_LO, DAS_C_HI)(const McScoreParams& p, int B, 
 }
 int DAS_CAT(dispatch_score_tma_, DAS_C_LO, DAS_C_HI)(const McTmaParams& p, int f, int ctas, cudaStream_t st) {
     return Range<DAS_C_LO>::score_tma(p, f, ctas, st);
+}
+int DAS_CAT(dispatch_score_up_, DAS_C_LO, DAS_C_HI)(const McUpParams& p, int f, int ctas, cudaStream_t st) {
+    return Range<DAS_C_LO>::score_up(p, f, ctas, st);
 }
 
 }  // namespace das

@@ -99,6 +99,32 @@ class MCState:
         self.n_passes += len(chunk)
         return self._pack(bufs, wl, sc)
 
+    def score_upsampled(self, pass_lowres_logits, labels: torch.Tensor | None, maps: Iterable[str] = (),
+                        scores: bool = True, weak_labels: bool = False,
+                        scores_out: torch.Tensor | None = None) -> dict:
+        """Fused K1+K2 on the model's LOW-RESOLUTION logits (das_mc_upsample_accumulate_finalize): every tensor
+        is the `low_res_x` [B,C,h,w] of one stochastic forward, i.e. what models/deeplab.py:59 feeds to
+        F.interpolate(..., size=(H,W), mode='bilinear', align_corners=True); the interpolation happens inside
+        the kernel.  The whole Monte-Carlo stack of the batch (<= 32 passes) arrives in this one call."""
+        if self.n_passes != 0:
+            raise DasError("score_upsampled() takes the whole Monte-Carlo stack of a batch in one call")
+        group = [pass_lowres_logits] if isinstance(pass_lowres_logits, torch.Tensor) else list(pass_lowres_logits)
+        chunk = [_need_cuda(t, "low-res logits", torch.float32) for t in group]
+        if not 1 <= len(chunk) <= min(_lib.MAX_PASS_GROUP, self.T_cap):
+            raise DasError(f"score_upsampled: {len(chunk)} passes, need 1..{min(_lib.MAX_PASS_GROUP, self.T_cap)}")
+        h, w = int(chunk[0].shape[-2]), int(chunk[0].shape[-1])
+        for t in chunk:
+            if tuple(t.shape) != (self.B, self.C, h, w):
+                raise DasError(f"low-res logits shape {tuple(t.shape)} != {(self.B, self.C, h, w)}")
+        labels, bufs, wl, sc = self._outputs(labels, maps, scores, weak_labels, scores_out)
+        arr = (C.c_void_p * len(chunk))(*[t.data_ptr() for t in chunk])
+        check(self.lib.das_mc_upsample_accumulate_finalize(C.byref(self.desc), _ptr(self.state), arr, len(chunk), h, w,
+                                                           _ptr(labels), *[_ptr(bufs.get(n)) for n in MAP_NAMES],
+                                                           _ptr(wl), _ptr(sc), _stream()),
+              "das_mc_upsample_accumulate_finalize")
+        self.n_passes += len(chunk)
+        return self._pack(bufs, wl, sc)
+
     def finalize(self, labels: torch.Tensor | None, maps: Iterable[str] = (), scores: bool = True,
                  weak_labels: bool = False, scores_out: torch.Tensor | None = None) -> dict:
         """-> {'scores': f32 [B,6] (column order _lib.SCORE_INDEX), <map name>: f32 [B,H,W], 'weak_labels': u8}.
@@ -147,6 +173,11 @@ class MCState:
         off = p.value - self.state.data_ptr()
         n = self.B * self.T_cap * self.H * self.W
         return self.state[off:off + n].view(self.B, self.T_cap, self.H, self.W).clone()
+
+
+def upsample_supported(h: int, w: int, H: int, W: int) -> bool:
+    """Can score_upsampled() interpolate h x w -> H x W in-kernel (else: F.interpolate + score())?"""
+    return bool(_lib.load().das_mc_upsample_supported(int(h), int(w), int(H), int(W)))
 
 
 # ---------------------------------------------------------------------------------------------

@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define DAS_ABI_VERSION 2
+#define DAS_ABI_VERSION 3
 
 typedef enum das_status {
     DAS_OK = 0,
@@ -132,6 +132,26 @@ int das_mc_accumulate_finalize(const das_mc_desc* desc, void* state, const float
                                int n_passes, int pass_begin, const float* labels, float* vote_entropy,
                                float* pred_entropy, float* bald, float* confidence, float* margin,
                                uint8_t* weak_labels, float* image_scores, void* stream);
+
+/* K1+K2 fused WITH the network's final bilinear upsample.  The reference model ends with
+ *     x = F.interpolate(low_res_x, size=input.size()[2:], mode='bilinear', align_corners=True)   models/deeplab.py:59
+ * (also models/unet.py:58, models/fastscnn.py:22); the selectors then reduce x (mc_dropout.py:40, ceal.py:111).
+ * This entry point takes `low_res_x` of every pass instead - f32 [B,C,h,w], HOST array of n_passes DEVICE
+ * pointers - interpolates to desc->H x desc->W inside the kernel with ATen's align_corners indices / weights
+ * (scale = float(h-1)/float(H-1), src = scale*dst, lerps as fma(l0, a, l1*b): bit-identical to ATen's vectorised
+ * CPU kernel at DeepLab's shapes) and runs the same reduction as das_mc_accumulate_finalize(pass_begin = 0):
+ * the full-resolution logits never exist in HBM (16x less traffic at stride 4).  All T = n_passes
+ * (<= DAS_MAX_PASS_GROUP) passes arrive in this one call; `state` only provides the block partials (any desc
+ * flags combination, DAS_MC_SINGLE_SHOT recommended).  Pointers need 4-byte alignment only.
+ * DAS_ERR_UNSUPPORTED when a 16-pixel output tile would read more than 6 source rows / columns (upsampling
+ * factors below ~3.75: query das_mc_upsample_supported first and use F.interpolate + das_mc_accumulate_finalize). */
+int das_mc_upsample_accumulate_finalize(const das_mc_desc* desc, void* state,
+                                        const float* const* pass_lowres_logits, int n_passes, int h, int w,
+                                        const float* labels, float* vote_entropy, float* pred_entropy,
+                                        float* bald, float* confidence, float* margin, uint8_t* weak_labels,
+                                        float* image_scores, void* stream);
+/* 1 if das_mc_upsample_accumulate_finalize handles the h x w -> H x W interpolation, else 0 (host only). */
+int das_mc_upsample_supported(int h, int w, int H, int W);
 
 /* Device pointer to the recorded votes, u8 [B,T_cap,H,W] (test / debugging aid). */
 int das_mc_votes_ptr(const das_mc_desc* desc, void* state, uint8_t** votes);

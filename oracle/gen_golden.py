@@ -124,6 +124,55 @@ def gen_mc(name, seed, N, T, C, H, W, block, k, batch_size):
     print(f"[golden] {name}: ve_scores[:4]={ve_scores[:4]} selected={paths_to_idx(chosen)}")
 
 
+def gen_upsample(name, seed, N, T, C, h, w, H, W, block, k, batch_size):
+    """The reference selectors on a model that ends like models/deeplab.py:58-59: low-resolution decoder logits
+    -> F.interpolate(bilinear, align_corners=True) -> MC vote entropy / CEAL scorers.  Stores the reference's
+    outputs and three interpolated class planes (0, C//2, C-1) of image 0, pass 0 (pins oracle.restate.bilinear_upsample_align_corners)."""
+    ref = ref_shim.load_reference()
+    torch = ref.torch
+    ref.constants.MC_STEPS = T
+    gs = list(range(N))
+    low = synth.pool_logits(seed, gs, T, C, h, w, block)
+    labels = synth.pool_labels(seed, gs, H, W, C, block * 4)
+    pool = ref_shim.LowResPool(low, labels, H, W)
+    paths = [str(i) for i in range(N)]
+    crop = H if H == W else -1
+
+    sel = ref.active_selection.get_active_selection_class("variance", C, pool, crop, batch_size)
+    cap = SortedCapture()
+    ref.mc_dropout.sorted = cap
+    chosen = sel.get_vote_entropy_for_images(ref_shim.make_replay_model(pool), paths, k)
+    del ref.mc_dropout.sorted
+    ve_scores = np.array(cap.calls[0][0], dtype=np.float32)
+    nb = min(batch_size, N)
+    ds = ref_shim.SyntheticPathsDataset(pool, paths[:nb], crop, include_labels=True)
+    image_batch = torch.stack([ds[i]["image"] for i in range(nb)])
+    label_batch = torch.stack([ds[i]["label"] for i in range(nb)])
+    maps = sel._get_vote_entropy_for_batch(ref_shim.make_replay_model(pool), image_batch, label_batch)
+    ve_maps = np.stack([m.numpy() for m in maps]).astype(np.float32)
+
+    ceal = ref.active_selection.get_active_selection_class("ceal_entropy", C, pool, crop, batch_size)
+    ent_sel, ent = ceal.get_maximum_entropy_samples(ref_shim.make_replay_model(pool), paths, k)
+    cap = SortedCapture()
+    ref.ceal.sorted = cap
+    conf_sel = ceal.get_least_confident_samples(ref_shim.make_replay_model(pool), paths, k)
+    marg_sel = ceal.get_least_margin_samples(ref_shim.make_replay_model(pool), paths, k)
+    del ref.ceal.sorted
+    up00 = torch.nn.functional.interpolate(torch.from_numpy(low[0, 0][None]), size=(H, W), mode="bilinear",
+                                           align_corners=True)[0].numpy()
+    np.savez_compressed(
+        os.path.join(GOLDEN, name + ".npz"),
+        meta=np.array([seed, N, T, C, h, w, H, W, block, k, batch_size], dtype=np.int64),
+        versions=versions(), lowres_sha=np.array(checksum(low)), labels_sha=np.array(checksum(labels)),
+        upsampled_image0_pass0_classes=up00[[0, C // 2, C - 1]].astype(np.float32),  # 3 class planes keep the file small
+        ve_scores=ve_scores, ve_selected=paths_to_idx(chosen), ve_maps=ve_maps,
+        ceal_entropy=np.array(ent, dtype=np.float32), ceal_entropy_selected=paths_to_idx(ent_sel),
+        ceal_conf=np.array(cap.calls[0][0], dtype=np.float32), ceal_conf_selected=paths_to_idx(conf_sel),
+        ceal_margin=np.array(cap.calls[1][0], dtype=np.float32), ceal_margin_selected=paths_to_idx(marg_sel),
+    )
+    print(f"[golden] {name}: ve_scores[:4]={ve_scores[:4]} selected={paths_to_idx(chosen)}")
+
+
 def gen_region(name, seed, N, T, C, S, block, R, selection_size, batch_size):
     """create_region_maps of mc_dropout (square crop S), with labelled-region suppression."""
     ref = ref_shim.load_reference()
@@ -376,6 +425,12 @@ FIXTURES = {
     "coreset_e2e": lambda: gen_coreset_e2e("coreset_e2e", synth.DEFAULT_SEED + 8, N=14, L=4, K=5, batch_size=4),
     "nms_png": gen_nms_png,
     "maxsubset": gen_maxsubset,
+    # fused final upsample: DeepLab-style exact x4 onto an odd crop (ATen's vectorised path) ...
+    "upsample_odd": lambda: gen_upsample("upsample_odd", synth.DEFAULT_SEED + 9, N=5, T=5, C=21, h=17, w=17, H=65, W=65, block=2, k=2, batch_size=3),
+    # ... the Cityscapes ratio (in-1)/(out-1) != 1/4 on an even, rectangular crop ...
+    "upsample_rect": lambda: gen_upsample("upsample_rect", synth.DEFAULT_SEED + 10, N=4, T=4, C=19, h=12, w=16, H=48, W=64, block=2, k=2, batch_size=2),
+    # ... and 33 -> 129 (3 x 3 tiles with ragged edges, 9 tiles deep windows)
+    "upsample_mid": lambda: gen_upsample("upsample_mid", synth.DEFAULT_SEED + 11, N=3, T=3, C=19, h=33, w=33, H=129, W=129, block=4, k=1, batch_size=2),
     "accuracy_small": lambda: gen_accuracy("accuracy_small", 41, 6, 5, 40, 8, 9, 4, 3),
 }
 

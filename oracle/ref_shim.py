@@ -82,6 +82,18 @@ class SyntheticPool:
         return self.logits.shape[-2:]
 
 
+class LowResPool(SyntheticPool):
+    """Pool whose `logits` are the decoder's LOW-RESOLUTION outputs [N,T,C,h,w]; images / labels are H x W."""
+
+    def __init__(self, logits, labels, H, W):
+        super().__init__(logits, labels)
+        self.full_hw = (H, W)
+
+    @property
+    def hw(self):
+        return self.full_hw
+
+
 class SyntheticPathsDataset:
     """Same constructor as the reference PathsDataset; yields {'image','label'} or the image.
 
@@ -139,6 +151,10 @@ def make_replay_model(pool: SyntheticPool, model_name: str = "deeplab"):
             if self.noisy_features:
                 self.noisy_calls += 1
             out = torch.from_numpy(np.stack([pool.logits[g, t % pool.logits.shape[1]] for g in gs]))
+            if isinstance(pool, LowResPool):
+                # the reference model's own last line (models/deeplab.py:59), verbatim in meaning: the stored
+                # logits play the role of `low_res_x`, the image size is the output size
+                out = torch.nn.functional.interpolate(out, size=x.size()[2:], mode='bilinear', align_corners=True)
             if self.return_features:
                 return out, torch.from_numpy(np.stack([pool.features[g] for g in gs]))
             return out

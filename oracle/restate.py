@@ -86,6 +86,51 @@ def margin_map(p: np.ndarray, valid: np.ndarray | None) -> np.ndarray:
     return m
 
 
+def _fma32(a, b, c):
+    """float32 fused multiply-add: a*b is exact in float64 (24 + 24 significand bits), one rounding to float64
+    and one to float32 follow (a double rounding that differs from a true fma in < 1e-9 of the cases)."""
+    return (np.asarray(a, np.float64) * np.asarray(b, np.float64) + np.asarray(c, np.float64)).astype(np.float32)
+
+
+def _align_corners_axis(n_in: int, n_out: int):
+    """ATen's source index / weights of one axis for mode='bilinear', align_corners=True
+    (aten/src/ATen/native/UpSample.h: area_pixel_compute_scale, area_pixel_compute_source_index,
+    guard_index_and_lambda; PyTorch 2.11 - not vendored in the reference, called from models/deeplab.py:59):
+    scale = float(in-1)/float(out-1) (0 if out == 1), src = scale*dst, i0 = min(int(src), in-1),
+    l1 = clamp(src - i0, 0, 1), l0 = 1 - l1, i1 = i0 + (i0 < in-1)."""
+    scale = np.float32(0) if n_out <= 1 else np.float32(n_in - 1) / np.float32(n_out - 1)
+    src = (scale * np.arange(n_out, dtype=np.float32)).astype(np.float32)
+    i0 = np.minimum(src.astype(np.int64), n_in - 1)
+    l1 = np.clip((src - i0.astype(np.float32)).astype(np.float32), np.float32(0), np.float32(1))
+    l0 = (np.float32(1) - l1).astype(np.float32)
+    i1 = i0 + (i0 < n_in - 1)
+    return i0, i1, l0, l1
+
+
+def bilinear_upsample_align_corners(low: np.ndarray, H: int, W: int) -> np.ndarray:
+    """F.interpolate(low, size=(H, W), mode='bilinear', align_corners=True) - the last op of the reference
+    models (models/deeplab.py:59, unet.py:58, fastscnn.py:22).  low float32 [..., h, w] -> [..., H, W].
+
+    out = l0y*(l0x*a + l1x*b) + l1y*(l0x*c + l1x*d), each sum evaluated as fma(l0, ., l1*.) - which is
+    bit-identical to ATen's vectorised CPU kernel (torch 2.11, AVX-512) for outputs such as 17->65, 33->129,
+    129->513 and 128x256->512x1024 (pinned by tests/golden/upsample_*.npz); on the tiny even-sized case in the
+    goldens ATen takes a differently rounded code path that is within 2 float32 ulp of this one."""
+    low = np.asarray(low, np.float32)
+    h, w = low.shape[-2:]
+    y0, y1, ly0, ly1 = _align_corners_axis(h, H)
+    x0, x1, lx0, lx1 = _align_corners_axis(w, W)
+    top, bot = low[..., y0, :], low[..., y1, :]
+    t = _fma32(lx0, top[..., x0], (lx1 * top[..., x1]).astype(np.float32))
+    b = _fma32(lx0, bot[..., x0], (lx1 * bot[..., x1]).astype(np.float32))
+    return _fma32(ly0[:, None], t, (ly1[:, None] * b).astype(np.float32))
+
+
+def mc_maps_upsampled(pass_lowres: np.ndarray, labels: np.ndarray | None, C: int, H: int, W: int) -> dict:
+    """mc_maps() of the model output the reference selectors see: the low-resolution decoder logits
+    [T,C,h,w] interpolated to H x W (models/deeplab.py:58-59), then mc_dropout.py:37-49 / ceal.py."""
+    return mc_maps(bilinear_upsample_align_corners(pass_lowres, H, W), labels, C)
+
+
 def mc_maps(pass_logits: np.ndarray, labels: np.ndarray | None, C: int) -> dict:
     """All per-pixel maps for one image.  pass_logits float32 [T,C,H,W].
 

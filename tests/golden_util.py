@@ -37,3 +37,16 @@ def regions_from_rows(rows, N):
     for i, r, c, h, w in rows.tolist():
         out[i].append((r, c, h, w))
     return out
+
+
+def upsample_case(name):
+    """-> (golden, meta dict, low-res logits [N,T,C,h,w], labels [N,H,W]) of an upsample_* fixture."""
+    g = load(name)
+    keys = ("seed", "N", "T", "C", "h", "w", "H", "W", "block", "k", "batch_size")
+    m = dict(zip(keys, (int(v) for v in g["meta"])))
+    gs = list(range(m["N"]))
+    low = synth.pool_logits(m["seed"], gs, m["T"], m["C"], m["h"], m["w"], m["block"])
+    labels = synth.pool_labels(m["seed"], gs, m["H"], m["W"], m["C"], m["block"] * 4)
+    assert sha(low) == str(g["lowres_sha"]) and sha(labels) == str(g["labels_sha"]), \
+        "synthetic input stream changed - regenerate goldens"
+    return g, m, low, labels

@@ -24,7 +24,7 @@ def test_library_loads_and_exports_every_declared_symbol():
     assert declared == set(_lib.EXPORTED_SYMBOLS)
     for name in declared:
         assert isinstance(getattr(lib, name), ctypes._CFuncPtr)
-    assert lib.das_abi_version() == _lib.ABI_VERSION == 2
+    assert lib.das_abi_version() == _lib.ABI_VERSION == 3
     assert lib.das_strerror(0) == b"ok" and b"invalid" in lib.das_strerror(-1)
     # argument validation happens before any CUDA call, so these are safe without a device
     nbytes = ctypes.c_size_t()

@@ -252,3 +252,47 @@ def _maxsubset_inputs(g, tag):
     Y[M // 3] = Y[M // 5]
     assert G.sha(X) == str(g[f"{tag}_x_sha"]) and G.sha(Y) == str(g[f"{tag}_y_sha"])
     return X, Y, k
+
+
+# ---- fused final upsample: models/deeplab.py:59 restated ------------------------
+
+UPSAMPLE_CASES = ("upsample_odd", "upsample_rect", "upsample_mid")
+
+
+@pytest.mark.parametrize("name", UPSAMPLE_CASES)
+def test_bilinear_restatement_matches_aten(name):
+    g, m, low, _ = G.upsample_case(name)
+    C = m["C"]
+    got = R.bilinear_upsample_align_corners(low[0, 0][[0, C // 2, C - 1]], m["H"], m["W"])
+    want = g["upsampled_image0_pass0_classes"]
+    if name == "upsample_rect":
+        # 12x16 -> 48x64: ATen rounds this small even-sized case differently (same weights, other association)
+        np.testing.assert_allclose(got, want, rtol=0, atol=2 * np.spacing(np.float32(np.abs(want).max())))
+    else:
+        np.testing.assert_array_equal(got, want)   # bit-exact at the DeepLab-style shapes
+
+
+@pytest.mark.parametrize("name", UPSAMPLE_CASES)
+def test_upsampled_scoring_matches_reference(name):
+    """reference selectors on F.interpolate(low_res_x) == restatement on bilinear_upsample_align_corners(low_res_x)"""
+    g, m, low, labels = G.upsample_case(name)
+    N, C, k = m["N"], m["C"], m["k"]
+    ve, ent, conf, marg = [], [], [], []
+    for i in range(N):
+        maps = R.mc_maps_upsampled(low[i], labels[i], C, m["H"], m["W"])
+        if i < g["ve_maps"].shape[0]:
+            # a vote can flip where two upsampled logits tie within an ulp: tolerate a handful of pixels
+            bad = ~np.isclose(maps["vote_entropy"], g["ve_maps"][i], rtol=RTOL, atol=ATOL)
+            assert bad.sum() <= (2 if name == "upsample_rect" else 0), bad.sum()
+        ve.append(R.image_scores(maps)["vote_entropy"])
+        single = R.image_scores(R.mc_maps_upsampled(low[i, :1], labels[i], C, m["H"], m["W"]))
+        ent.append(single["pred_entropy"]), conf.append(single["confidence"]), marg.append(single["margin"])
+    vtol = 1e-5 if name == "upsample_rect" else 1e-7
+    np.testing.assert_allclose(ve, g["ve_scores"], rtol=RTOL, atol=vtol)
+    np.testing.assert_allclose(ent, g["ceal_entropy"], rtol=RTOL, atol=1e-7)
+    np.testing.assert_allclose(conf, g["ceal_conf"], rtol=RTOL, atol=1e-7)
+    np.testing.assert_allclose(marg, g["ceal_margin"], rtol=RTOL, atol=1e-7)
+    assert R.rank_topk(ve, k, True) == g["ve_selected"].tolist()
+    assert R.rank_topk(ent, k, True) == g["ceal_entropy_selected"].tolist()
+    assert R.rank_topk(conf, k, False) == g["ceal_conf_selected"].tolist()
+    assert R.rank_topk(marg, k, False) == g["ceal_margin_selected"].tolist()
