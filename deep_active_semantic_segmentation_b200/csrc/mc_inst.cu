@@ -167,10 +167,10 @@ template <int C>
 int launch_score_up(const McUpParams& p, int flags, int ctas_per_sm, cudaStream_t st) {
     const bool probs = flags & DAS_MC_PROBS, votes = flags & DAS_MC_VOTES;
     if (ctas_per_sm <= 0) ctas_per_sm = up_ctas_per_sm(C);
-    // ring depth: the windows are small (C * 192 bytes), 4 stages keep one producer round trip ahead of the consumers
+    // ring depth: the windows are small (C * 144 bytes), 4 stages keep one producer round trip ahead of the consumers
     McUpParams q = p;
     q.stages = 4;
-    const size_t smem = 2 * up_rows_bytes(C) + (size_t)q.stages * up_stage_bytes(C);
+    const size_t smem = up_rows_bytes(C) + (size_t)q.stages * up_stage_bytes(C);
     const int tiles = p.B * p.tiles_x * p.tiles_y;
 #define DAS_UP(P, Q)                                                                               \
     do {                                                                                           \

@@ -4,13 +4,15 @@
 // read from HBM: the kernel reads [B,C,h,w] (16x fewer bytes at DeepLab's stride-4 decoder), so the step is no
 // longer HBM bound but issue bound, and the interpolation is organised to cost as few issue slots as possible:
 //
-//   tile      16 x 16 output pixels; 128 consumer threads own a horizontal pixel pair each (as in mc_tma.cuh)
+//   tile      16 x 16 output pixels per CTA; each of the 4 consumer warps owns a 16-row x 4-column strip, a lane
+//             owns a horizontal pixel pair of one row (accumulators in registers, as in mc_tma.cuh)
 //   producer  one warp copies the <= 6 x 6 low-res source window of every class into a shared-memory ring
 //             (4-byte cp.async: no alignment demands, works for 129 x 129 planes) and signals an mbarrier
-//   phase 1   the consumers interpolate HORIZONTALLY once per source row: rows[c][r][16 px], r < 6 - shared by the
-//             ~4 output rows that lie between the same two source rows (7 instructions per pixel pair and source
-//             row, 6/16 of them per output pixel pair)
-//   phase 2   a thread reads the two interpolated rows around its pixel pair (2 LDS.64) and interpolates
+//   phase 1   a warp interpolates HORIZONTALLY, once per source row, the 4 columns of its strip:
+//             rows[warp][c][r < 6][4 px] - shared by the ~4 output rows that lie between the same two source rows
+//             (7 instructions per pixel pair and source row, 6/16 of them per output pixel pair).  The strip is
+//             warp-private: __syncwarp() orders the two phases, there is no CTA barrier inside the pass loop
+//   phase 2   a lane reads the two interpolated rows around its pixel pair (2 LDS.64) and interpolates
 //             VERTICALLY with packed FMUL2 + FFMA2: 3 extra instructions per class and pass over the TMA kernel
 //
 // Arithmetic: indices and weights exactly as ATen's align_corners path (area_pixel_compute_scale /
@@ -24,7 +26,9 @@ namespace das {
 
 constexpr int kUpTile = 16;                 // output tile edge
 constexpr int kUpRows = 6;                  // source rows / columns a tile may touch (host-checked per shape)
-constexpr int kUpColsPad = 8;               // row stride of the staged source window (floats)
+constexpr int kUpCols = 6;                  // row stride of the staged window (floats): stride 6 keeps the
+                                            // phase-1 reads of 16 (class,row) items x 2 columns on 32 distinct banks
+constexpr int kUpStrip = 4;                 // columns per consumer warp
 constexpr int kUpThreads = 160;             // 4 consumer warps + 1 producer warp
 constexpr int kUpMaxStages = 8;
 
@@ -37,7 +41,7 @@ struct McUpParams {
 };
 
 constexpr int up_ctas_per_sm(int C) { return C <= 24 ? 3 : 2; }
-constexpr size_t up_stage_bytes(int C) { return (size_t)C * kUpRows * kUpColsPad * sizeof(float); }
+constexpr size_t up_stage_bytes(int C) { return (size_t)C * kUpRows * kUpCols * sizeof(float); }
 constexpr size_t up_rows_bytes(int C) { return (size_t)C * kUpRows * kUpTile * sizeof(float); }
 
 // ATen: source index and the weight of the upper neighbour for destination index d (align_corners=True)
@@ -54,9 +58,9 @@ __global__ void __launch_bounds__(kUpThreads, up_ctas_per_sm(C)) mc_score_up_ker
     constexpr int NT = 128, VEC = 2;
     constexpr int CR = C * kUpRows;                         // (class, source row) pairs per tile
     constexpr int P1_ITERS = (CR + 15) / 16;                // phase-1 items per thread
-    constexpr uint32_t kStageBytes = (uint32_t)(C * kUpRows * kUpColsPad * sizeof(float));
+    constexpr uint32_t kStageBytes = (uint32_t)(C * kUpRows * kUpCols * sizeof(float));
     constexpr uint32_t kRowsBytes = (uint32_t)(C * kUpRows * kUpTile * sizeof(float));
-    extern __shared__ __align__(16) uint8_t smem[];         // [2][C][6][16] interpolated rows | ring of [C][6][8] windows
+    extern __shared__ __align__(16) uint8_t smem[];         // [4 warps][C][6][4] interpolated rows | ring of [C][6][6] windows
     __shared__ uint64_t bars[2 * kUpMaxStages];
     __shared__ uint32_t hist32[VOTES ? C * NT * VEC / 4 + 1 : 1];
     __shared__ float lut[VOTES ? 256 : 1];
@@ -66,7 +70,7 @@ __global__ void __launch_bounds__(kUpThreads, up_ctas_per_sm(C)) mc_score_up_ker
     const McFinParams& f = q.fin;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int S = q.stages, T = q.n_passes;
-    const uint32_t ring0 = tma_smem_u32(smem) + 2u * kRowsBytes, bar0 = tma_smem_u32(bars);
+    const uint32_t ring0 = tma_smem_u32(smem) + kRowsBytes, bar0 = tma_smem_u32(bars);
     const int tiles_per_image = q.tiles_x * q.tiles_y;
     const int total_tiles = q.B * tiles_per_image;
 
@@ -80,9 +84,10 @@ __global__ void __launch_bounds__(kUpThreads, up_ctas_per_sm(C)) mc_score_up_ker
     __syncthreads();
 
     if (warp == 4) {
-        // ===== producer warp: lane -> up to two slots (row, col) of the 6 x 8 window, one cp.async per class =====
-        const int s0 = lane, s1 = lane + 32;                  // slot = row * 8 + col
-        const bool v0 = (s0 & 7) < kUpRows, v1 = s1 < kUpRows * kUpColsPad && (s1 & 7) < kUpRows;
+        // ===== producer warp: lane -> up to two slots (row, col) of the 6 x 6 window, one cp.async per class =====
+        constexpr int kSlots = kUpRows * kUpCols;            // 36 floats per class: slot = row * 6 + col
+        const int s0 = lane, s1 = lane + 32;
+        const bool v1 = s1 < kSlots;
         const size_t plane = (size_t)q.h * q.w;
         int stage = 0;
         uint32_t phase = 0;
@@ -92,20 +97,19 @@ __global__ void __launch_bounds__(kUpThreads, up_ctas_per_sm(C)) mc_score_up_ker
             const int r_base = min((int)__fmul_rn(q.rh, (float)ty0), q.h - 1);
             const int c_base = min((int)__fmul_rn(q.rw, (float)tx0), q.w - 1);
             // clamped source coordinates: slots past the plane edge repeat the edge (never used with weight > 0)
-            const uint32_t off0 = (uint32_t)(min(r_base + (s0 >> 3), q.h - 1) * q.w + min(c_base + (s0 & 7), q.w - 1));
-            const uint32_t off1 = (uint32_t)(min(r_base + (s1 >> 3), q.h - 1) * q.w + min(c_base + (s1 & 7), q.w - 1));
+            const uint32_t off0 = (uint32_t)(min(r_base + s0 / kUpCols, q.h - 1) * q.w + min(c_base + s0 % kUpCols, q.w - 1));
+            const uint32_t off1 = (uint32_t)(min(r_base + s1 / kUpCols, q.h - 1) * q.w + min(c_base + s1 % kUpCols, q.w - 1));
             for (int g = 0; g < T; ++g) {
                 tma_mbar_wait(bar0 + 8u * (S + stage), phase ^ 1u);
                 const float* src = q.lowres[g] + (size_t)b * C * plane;
                 const uint32_t dst = ring0 + stage * kStageBytes;
 #pragma unroll 1
                 for (int c = 0; c < C; ++c) {
-                    if (v0)
-                        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst + (uint32_t)(c * 48 + s0) * 4u),
-                                     "l"(src + off0)
-                                     : "memory");
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst + (uint32_t)(c * kSlots + s0) * 4u),
+                                 "l"(src + off0)
+                                 : "memory");
                     if (v1)
-                        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst + (uint32_t)(c * 48 + s1) * 4u),
+                        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst + (uint32_t)(c * kSlots + s1) * 4u),
                                      "l"(src + off1)
                                      : "memory");
                     src += plane;
@@ -118,7 +122,7 @@ __global__ void __launch_bounds__(kUpThreads, up_ctas_per_sm(C)) mc_score_up_ker
         return;
     }
 
-    // ===== consumers: 128 threads; thread -> pixel pair (x, x+1) of row y inside the 16 x 16 tile =====
+    // ===== consumers: warp -> columns [4 warp, 4 warp + 4) of the 16 x 16 tile; lane -> pixel pair (x, x+1) of row yy =====
     const SyncNamed<NT> sync;
     if (VOTES) {
         const float Tf = (float)f.T;
@@ -128,14 +132,15 @@ __global__ void __launch_bounds__(kUpThreads, up_ctas_per_sm(C)) mc_score_up_ker
         }
         sync();
     }
-    const int xp = tid & 7, yy = tid >> 3;
+    const int xp = lane & 1, yy = lane >> 1;
+    float* rows = reinterpret_cast<float*>(smem) + warp * (C * kUpRows * kUpStrip);  // warp-private
     const bool vec_ok = (q.W & 1) == 0;  // pixel pairs are 8-byte aligned in the maps
     int stage = 0;
-    uint32_t phase = 0, it = 0;
+    uint32_t phase = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const int b = tile / tiles_per_image, t_in = tile % tiles_per_image;
         const int ty0 = (t_in / q.tiles_x) * kUpTile, tx0 = (t_in % q.tiles_x) * kUpTile;
-        const int y = ty0 + yy, x = tx0 + 2 * xp;
+        const int y = ty0 + yy, x = tx0 + kUpStrip * warp + 2 * xp;
         bool act[VEC];
         act[0] = y < q.H && x < q.W;
         act[1] = y < q.H && x + 1 < q.W;
@@ -145,19 +150,19 @@ __global__ void __launch_bounds__(kUpThreads, up_ctas_per_sm(C)) mc_score_up_ker
         int y0, ys;
         float ly0, ly1;
         up_source(q.rh, min(y, q.H - 1), q.h, y0, ys, ly0, ly1);
-        const int top_idx = (y0 - r_base) * kUpTile + 2 * xp;  // float index inside the interpolated rows of class 0
-        const int bot_idx = top_idx + ys * kUpTile;
+        const int top_idx = (y0 - r_base) * kUpStrip + 2 * xp;  // float index inside the interpolated rows of class 0
+        const int bot_idx = top_idx + ys * kUpStrip;
         float lx0[VEC], lx1[VEC];
-        int a_idx[VEC], b_idx[VEC];  // the two source columns of pixel j inside window row yy (float index)
+        int a_idx[VEC], b_idx[VEC];  // the two source columns of pixel j inside (class, row) item yy (float index)
 #pragma unroll
         for (int j = 0; j < VEC; ++j) {
             int x0, xs;
             up_source(q.rw, min(x + j, q.W - 1), q.w, x0, xs, lx0[j], lx1[j]);
-            a_idx[j] = yy * kUpColsPad + (x0 - c_base);
+            a_idx[j] = yy * kUpCols + (x0 - c_base);
             b_idx[j] = a_idx[j] + xs;
         }
         const f32x2 LX0 = {lx0[0], lx0[1]}, LX1 = {lx1[0], lx1[1]}, LY0 = {ly0, ly0}, LY1 = {ly1, ly1};
-        const int h_store = yy * kUpTile + 2 * xp;
+        const int h_store = yy * kUpStrip + 2 * xp;
 
         if (VOTES) {
 #pragma unroll
@@ -172,19 +177,19 @@ __global__ void __launch_bounds__(kUpThreads, up_ctas_per_sm(C)) mc_score_up_ker
         for (int c = 0; c < C; ++c) acc.set(c, z);
         uint32_t first_vote = 0;
 
-        for (int g = 0; g < T; ++g, ++it) {
-            float* rows = reinterpret_cast<float*>(smem + (it & 1u) * kRowsBytes);
-            // ---- phase 1: horizontal interpolation of the staged window, (class, row) pairs yy, yy+16, ... ----
+        for (int g = 0; g < T; ++g) {
+            // ---- phase 1: horizontal interpolation of the staged window, (class, row) items yy, yy+16, ... ----
             tma_mbar_wait(bar0 + 8u * stage, phase);
+            __syncwarp();  // every lane has read the previous pass's rows
             {
-                const float* win = reinterpret_cast<const float*>(smem + 2u * kRowsBytes + stage * kStageBytes);
+                const float* win = reinterpret_cast<const float*>(smem + kRowsBytes + stage * kStageBytes);
 #pragma unroll
                 for (int k = 0; k < P1_ITERS; ++k) {
                     if (k * 16 + yy < CR) {
-                        const float* wk = win + k * 16 * kUpColsPad;
+                        const float* wk = win + k * 16 * kUpCols;
                         const f32x2 a = {wk[a_idx[0]], wk[a_idx[1]]}, bb = {wk[b_idx[0]], wk[b_idx[1]]};
                         const f32x2 r = fma2(LX0, a, mul2(LX1, bb));
-                        *reinterpret_cast<float2*>(rows + h_store + k * 16 * kUpTile) = make_float2(r.x, r.y);
+                        *reinterpret_cast<float2*>(rows + h_store + k * 16 * kUpStrip) = make_float2(r.x, r.y);
                     }
                 }
             }
@@ -192,13 +197,12 @@ __global__ void __launch_bounds__(kUpThreads, up_ctas_per_sm(C)) mc_score_up_ker
             if (lane == 0)  // this warp no longer reads the window: hand the slot back to the producer
                 asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar0 + 8u * (S + stage)) : "memory");
             if (++stage == S) stage = 0, phase ^= 1u;
-            sync();  // rows[it & 1] complete; rows[(it + 1) & 1] is free once every thread is past this barrier
             // ---- phase 2: vertical interpolation -> the C logits of this thread's two pixels ----
             float xl[C][VEC];
 #pragma unroll
             for (int c = 0; c < C; ++c) {
-                const float2 t = *reinterpret_cast<const float2*>(rows + top_idx + c * kUpRows * kUpTile);
-                const float2 u = *reinterpret_cast<const float2*>(rows + bot_idx + c * kUpRows * kUpTile);
+                const float2 t = *reinterpret_cast<const float2*>(rows + top_idx + c * kUpRows * kUpStrip);
+                const float2 u = *reinterpret_cast<const float2*>(rows + bot_idx + c * kUpRows * kUpStrip);
                 const f32x2 v = fma2(LY0, f32x2{t.x, t.y}, mul2(LY1, f32x2{u.x, u.y}));
                 xl[c][0] = v.x, xl[c][1] = v.y;
             }
