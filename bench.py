@@ -58,6 +58,7 @@ def parse():
                          "513x513, C=21, T=20, pool 10582, top-60 (odd planes: flat 1-D TMA maps)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-upsample-variant", action="store_true")
     return ap.parse_args()
 
 
@@ -263,9 +264,15 @@ def run_b200(args):
     e2e = None if args.no_e2e else run_e2e(args, world, rank, dev)
     cpu = None
     torch_gpu = None
+    fused_up = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu = cpu_baseline([p[:1].cpu() for p in passes], labels[:1].cpu(), budget_s=20.0)
         torch_gpu = torch_gpu_baseline(passes, labels)
+    if rank == 0 and world == 1 and not args.no_upsample_variant:
+        try:
+            fused_up = fused_upsample_variant(args, dev)
+        except Exception as exc:  # informative only: never lose the headline line
+            fused_up = {"error": repr(exc)[:200]}
 
     if rank == 0:
         line = {
@@ -278,7 +285,8 @@ def run_b200(args):
                                   "probs": "pred_entropy+bald+confidence+margin"}[args.mode],
                        "sharding": f"by image, {world} rank(s), candidate all-gather only",
                        "l2": f"inputs {T * B * C * H * W * 4 / 1e9:.2f} GB per step >> 126 MB L2 (no flush needed)"},
-            "roofline": roofline, "cpu_baseline": cpu, "torch_gpu_baseline": torch_gpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+            "roofline": roofline, "cpu_baseline": cpu, "torch_gpu_baseline": torch_gpu, "e2e": e2e,
+            "fused_upsample_variant": fused_up, "gpu_launches": int(launches), "clocks": clocks,
             "selected_head": [int(v) for v in (chosen[:5].tolist() if hasattr(chosen, "tolist") else chosen[:5])],
         }
         print(json.dumps(line), flush=True)
@@ -393,6 +401,95 @@ def run_e2e(args, world, rank, dev):
             "d2h_bytes_per_step": B * 6 * 4 + min(TOPK, B) * 12, "steps": K, "batch_images_per_step": B,
             "api": "ActiveSelectionMCDropout.get_mc_scores_for_images(model, images, k)",
             "note": "logits for every pass copied from pinned host memory (PCIe bound)"}
+
+
+def fused_upsample_variant(args, dev, steps=60):
+    """SURVEY 8(f)-1, reported next to the headline (rank 0, N = 1): the same pool step when the network hands over
+    its LOW-RESOLUTION decoder logits [B,C,H/4,W/4] (models/deeplab.py:58) and the final bilinear upsample
+    (models/deeplab.py:59) runs inside the scoring kernel - device-resident, and end to end through the selector
+    with the low-resolution logits of every pass coming from pinned host memory."""
+    import torch
+    from deep_active_semantic_segmentation_b200 import _lib, constants, ops, synth
+    from deep_active_semantic_segmentation_b200.active_selection import ActiveSelectionMCDropout, base
+
+    B = args.batch
+    h, w = (H + 3) // 4, (W + 3) // 4               # DeepLab's stride-4 decoder: 128 x 256 / 129 x 129
+    if not ops.upsample_supported(h, w, H, W):
+        return {"unavailable": f"{h}x{w} -> {H}x{W} is outside the fused kernel's range"}
+    low, lab_low = synth.device_pass_logits(synth.DEFAULT_SEED + 3, 0, B, T, C, h, w, dev, block=8)
+    labels = torch.nn.functional.interpolate(lab_low[:, None], size=(H, W), mode="nearest")[:, 0].contiguous()
+    votes, probs = args.mode in ("full", "votes"), args.mode in ("full", "probs")
+    st = ops.MCState(B, C, H, W, T, votes=votes, probs=probs, device=dev, single_shot=True)
+    scores = torch.zeros((B, _lib.N_SCORES), dtype=torch.float32, device=dev)
+
+    def step():
+        st.reset()
+        st.score_upsampled(low, labels, maps=(), scores_out=scores)
+
+    for _ in range(5):
+        step()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    out = {"value": round(B / ms * 1e3, 1), "unit": UNIT, "ms_per_step": round(ms, 4), "steps": steps,
+           "kernel": "mc_score_up_kernel (fused bilinear upsample + K1 + K2)", "lowres": [h, w],
+           "bound": "issue slots / latency (not HBM)", "hbm_bytes_per_step": T * B * C * h * w * 4,
+           "fullres_bytes_avoided_per_step": 2 * T * B * C * H * W * 4,
+           "note": "the network no longer writes T*B*C*H*W*4 bytes of interpolated logits and the scorer no longer reads them"}
+    if args.no_e2e:
+        return out
+    # end to end: low-resolution logits of every pass from pinned host memory through the selector API
+    Be, Ke = args.e2e_batch, 4 * args.e2e_steps
+    host = [torch.empty((Be,) + tuple(p.shape[1:]), dtype=p.dtype, pin_memory=True).copy_(p[:Be]) for p in low]
+    host_labels = torch.empty((Be, H, W), dtype=torch.float32, pin_memory=True).copy_(labels[:Be])
+    host_image = torch.zeros(3, H, W).pin_memory()
+
+    class HostDataset(torch.utils.data.Dataset):
+        def __init__(self, env, paths, crop_size, include_labels=False):
+            self.paths = paths
+
+        def __len__(self):
+            return len(self.paths)
+
+        def __getitem__(self, i):
+            return {"image": host_image, "label": host_labels[int(self.paths[i]) % Be]}
+
+    class HostLowResModel(torch.nn.Module):       # a forward that stops at `low_res_x`; its values arrive from the host
+        def __init__(self):
+            super().__init__()
+            self.drop = torch.nn.Dropout2d(0.25)
+            self.t = 0
+
+        def forward(self, x):
+            out = host[self.t % T].to(dev, non_blocking=True)
+            self.t += 1
+            return out[:x.shape[0]]
+
+    old_ds, old_T = base.paths_dataset.PathsDataset, constants.MC_STEPS
+    base.paths_dataset.PathsDataset, constants.MC_STEPS = HostDataset, T
+    try:
+        sel = ActiveSelectionMCDropout(C, None, -1, Be)
+        model = HostLowResModel().to(dev)
+        images = [str(i) for i in range(Ke * Be)]
+        sel.get_mc_scores_for_images(model, images[:Be], TOPK)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        sel.get_mc_scores_for_images(model, images, TOPK)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+    finally:
+        base.paths_dataset.PathsDataset, constants.MC_STEPS = old_ds, old_T
+    out["e2e"] = {"value": round(Ke * Be / dt, 2), "unit": UNIT, "steps": Ke, "batch_images_per_step": Be,
+                  "h2d_bytes_per_step": T * Be * C * h * w * 4 + Be * H * W * 4 + Be * 3 * H * W * 4,
+                  "d2h_bytes_per_step": Be * 6 * 4 + min(TOPK, Be) * 12,
+                  "api": "ActiveSelectionMCDropout.get_mc_scores_for_images(model, images, k), model returns low_res_x",
+                  "note": "low-resolution logits of every pass, images and labels copied from pinned host memory"}
+    return out
 
 
 def cpu_baseline(pass_logits_1img, labels_1img, budget_s: float):

@@ -74,28 +74,43 @@ class ActiveSelectionBase:
         return DataLoader(ds, batch_size=self.dataloader_batch_size, shuffle=False, num_workers=0)
 
     # -- Monte-Carlo scoring of one batch --------------------------------------------------------
-    def _group_size(self, T, logits):
+    def _group_size(self, T, per_pass_bytes):
         if self.pass_group is not None:
             return max(1, min(int(self.pass_group), T))
-        per_pass = logits.numel() * logits.element_size()
-        return max(1, min(T, MAX_PASS_GROUP, self.pass_group_bytes // max(per_pass, 1)))
+        return max(1, min(T, MAX_PASS_GROUP, self.pass_group_bytes // max(int(per_pass_bytes), 1)))
 
     def _mc_batch(self, forward, image_batch, label_batch, T, votes, probs, maps=(), weak_labels=False):
         """T calls of `forward(image_batch)`; the logits are consumed in groups of G passes: all but the last
         group by K1 (das_mc_accumulate), the last group by the fused K1+K2 kernel
-        (das_mc_accumulate_finalize).  G == T: nothing but the logits ever crosses HBM."""
+        (das_mc_accumulate_finalize).  G == T: nothing but the logits ever crosses HBM.
+
+        A model that returns its LOW-RESOLUTION decoder logits (`low_res_x` of models/deeplab.py:58, i.e. the
+        forward without its last line `F.interpolate(low_res_x, size=input.size()[2:], mode='bilinear',
+        align_corners=True)`) is recognised by the spatial size of its output: the interpolation then happens
+        inside the scoring kernel (das_mc_upsample_accumulate_finalize) and the full-resolution logits never
+        exist in HBM.  Shapes the fused kernel does not take (upsampling factors below ~3.75, T > 32) are
+        interpolated by torch on the device - the model's own last op - and scored by the resident-logits kernels."""
         B, _, H, W = image_batch.shape
         state, G = None, 1
         pending = []
+        lowres = fuse = False
         with torch.no_grad():
             for step in range(T):
                 logits = forward(image_batch)
                 if state is None:
-                    G = self._group_size(T, logits)
+                    h, w = int(logits.shape[-2]), int(logits.shape[-1])
+                    lowres = (h, w) != (H, W)
+                    fuse = lowres and T <= MAX_PASS_GROUP and ops.upsample_supported(h, w, H, W)
+                    G = T if fuse else self._group_size(T, B * logits.shape[1] * H * W * logits.element_size())
                     state = ops.MCState(B, logits.shape[1], H, W, T, votes=votes, probs=probs, device=logits.device,
                                         single_shot=(G >= T))
+                if lowres and not fuse:
+                    logits = torch.nn.functional.interpolate(logits, size=(H, W), mode='bilinear', align_corners=True)
                 pending.append(logits)
                 if step == T - 1:
+                    if fuse:
+                        return state.score_upsampled(pending, label_batch, maps=maps, scores=True,
+                                                     weak_labels=weak_labels)
                     return state.score(pending, label_batch, maps=maps, scores=True, weak_labels=weak_labels)
                 if len(pending) >= G:
                     state.accumulate(pending)

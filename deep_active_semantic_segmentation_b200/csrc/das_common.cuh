@@ -70,6 +70,15 @@ __device__ __forceinline__ float rcp_approx(float x) {
     return y;
 }
 
+// MUFU.LG2 alone: absolute error <= 2^-22 for arguments in (0.5, 2), relative error <= 2^-22 elsewhere.  Used for
+// log2 of the softmax denominator (s in [1, C]) in the per-pass entropy, which only feeds the composed scores
+// (expected entropy, BALD); the reference-pinned formulas (-sum p log2(p + 1e-12)) keep log2f.
+__device__ __forceinline__ float lg2_approx(float x) {
+    float y;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
 // Blackwell packed fp32: one FFMA2 / FADD2 / FMUL2 issue slot does two IEEE fp32 operations (lane-wise, same
 // rounding as the scalar instructions).  The kernels that own pixel PAIRS use them to halve the issue
 // slots of the softmax arithmetic.

@@ -119,7 +119,7 @@ McLayout mc_layout(const das_mc_desc& d) {
     // sized for the finest block partition any kernel uses (the TMA kernel: 256-pixel tiles)
     const int blocks_tma = (int)((HW + kTmaFlatPix - 1) / kTmaFlatPix);
     // ... and the fused-upsample kernel: 16 x 16 tiles
-    const int blocks_up = ((d.H + kUpTile - 1) / kUpTile) * ((d.W + kUpTile - 1) / kUpTile);
+    const int blocks_up = ((d.H + kUpTileH - 1) / kUpTileH) * ((d.W + up_tile_w(4) - 1) / up_tile_w(4));
     int blocks_max = L.blocks_fused > blocks_tma ? L.blocks_fused : blocks_tma;
     if (blocks_up > blocks_max) blocks_max = blocks_up;
     off += align_up((size_t)d.B * blocks_max * DAS_N_SCORES * sizeof(float), 256);
@@ -281,19 +281,41 @@ static McUpParams g_up_params;
 
 // ATen's align_corners scale (area_pixel_compute_scale<float>)
 static float up_scale(int n_in, int n_out) { return n_out > 1 ? (float)(n_in - 1) / (float)(n_out - 1) : 0.f; }
-// does every 16-pixel tile of the output axis read at most kUpRows consecutive source samples?  (the kernel's
-// arithmetic, replayed on the host: IEEE float multiply, truncation)
-static bool up_window_fits(int n_in, int n_out, float scale) {
-    for (int t0 = 0; t0 < n_out; t0 += kUpTile) {
-        const int last = (t0 + kUpTile - 1 < n_out ? t0 + kUpTile - 1 : n_out - 1);
-        int base = (int)(scale * (float)t0);
-        if (base > n_in - 1) base = n_in - 1;
-        int i0 = (int)(scale * (float)last);
-        if (i0 > n_in - 1) i0 = n_in - 1;
+// does every `tile`-pixel tile of the output axis read at most `window` consecutive source samples, and does a
+// 4-pixel strip (tile % 4 == 0) start at most one source sample after its first pixel's?  (the kernel's arithmetic,
+// replayed on the host: IEEE float multiply, truncation)
+static bool up_window_fits(int n_in, int n_out, float scale, int tile, int window) {
+    auto src = [&](int d) {
+        int i = (int)(scale * (float)d);
+        return i > n_in - 1 ? n_in - 1 : i;
+    };
+    for (int t0 = 0; t0 < n_out; t0 += tile) {
+        const int last = (t0 + tile - 1 < n_out ? t0 + tile - 1 : n_out - 1);
+        const int i0 = src(last);
         const int i1 = i0 + (i0 < n_in - 1 ? 1 : 0);
-        if (i1 - base > kUpRows - 1) return false;
+        if (i1 - src(t0) > window - 1) return false;
+    }
+    for (int s0 = 0; s0 < n_out; s0 += kUpStrip) {
+        const int last = (s0 + kUpStrip - 1 < n_out ? s0 + kUpStrip - 1 : n_out - 1);
+        if (src(last) - src(s0) > 1) return false;
     }
     return true;
+}
+static bool up_supported(int h, int w, int H, int W, int nw) {
+    if (h < 1 || w < 1 || H < 1 || W < 1) return false;
+    return up_window_fits(h, H, up_scale(h, H), kUpTileH, kUpRows) &&
+           up_window_fits(w, W, up_scale(w, W), up_tile_w(nw), up_win_cols(nw));
+}
+// consumer warps per CTA (0 = the shape is not supported).  15 (one 512-thread CTA per SM, tile 16 x 60, one
+// producer warp per SM) measured 3-8 % faster than 4 (three 160-thread CTAs per SM, tile 16 x 16) on 512 x 1024 and
+// 513 x 513 outputs (profiles/r1_upsample_notes.md); narrow outputs keep the small tile.  DAS_MC_UP_WARPS = 4 | 15
+// overrides the choice.
+static int up_warps(int h, int w, int H, int W) {
+    const char* e = getenv("DAS_MC_UP_WARPS");
+    const int v = e != nullptr ? atoi(e) : 0;
+    if (v == 4 || v == 15) return up_supported(h, w, H, W, v) ? v : 0;
+    if (W >= 2 * up_tile_w(15) && up_supported(h, w, H, W, 15)) return 15;
+    return up_supported(h, w, H, W, 4) ? 4 : 0;
 }
 
 extern "C" {
@@ -389,8 +411,7 @@ int das_mc_accumulate_finalize(const das_mc_desc* desc, void* state, const float
 }
 
 int das_mc_upsample_supported(int h, int w, int H, int W) {
-    if (h < 1 || w < 1 || H < 1 || W < 1) return 0;
-    return up_window_fits(h, H, up_scale(h, H)) && up_window_fits(w, W, up_scale(w, W)) ? 1 : 0;
+    return up_warps(h, w, H, W) != 0 ? 1 : 0;
 }
 
 int das_mc_upsample_accumulate_finalize(const das_mc_desc* desc, void* state, const float* const* pass_lowres_logits,
@@ -402,11 +423,12 @@ int das_mc_upsample_accumulate_finalize(const das_mc_desc* desc, void* state, co
     if (pass_lowres_logits == nullptr || h < 1 || w < 1) return DAS_ERR_INVALID_ARG;
     if (n_passes < 1 || n_passes > desc->T_cap) return DAS_ERR_INVALID_ARG;
     if (n_passes > DAS_MAX_PASS_GROUP) return DAS_ERR_UNSUPPORTED;
-    if (!das_mc_upsample_supported(h, w, desc->H, desc->W)) return DAS_ERR_UNSUPPORTED;
+    const int nw = up_warps(h, w, desc->H, desc->W);
+    if (nw == 0) return DAS_ERR_UNSUPPORTED;
     // source offsets inside one image are formed in 32 bits
     if ((unsigned long long)desc->C * h * w >= (1ull << 31)) return DAS_ERR_UNSUPPORTED;
     McUpParams& q = g_up_params;
-    const int tiles_x = (desc->W + kUpTile - 1) / kUpTile, tiles_y = (desc->H + kUpTile - 1) / kUpTile;
+    const int tiles_x = (desc->W + up_tile_w(nw) - 1) / up_tile_w(nw), tiles_y = (desc->H + kUpTileH - 1) / kUpTileH;
     rc = fill_fin_params(desc, state, labels, n_passes, vote_entropy, pred_entropy, bald, confidence, margin,
                          weak_labels, tiles_x * tiles_y, &q.fin);
     if (rc != DAS_OK) return rc;
@@ -422,7 +444,7 @@ int das_mc_upsample_accumulate_finalize(const das_mc_desc* desc, void* state, co
     q.tiles_x = tiles_x, q.tiles_y = tiles_y;
     q.rh = up_scale(h, desc->H), q.rw = up_scale(w, desc->W);
     cudaStream_t st = (cudaStream_t)stream;
-    rc = dispatch_score_up(q, desc->flags & (DAS_MC_VOTES | DAS_MC_PROBS), tma_ctas_per_sm(), st);
+    rc = dispatch_score_up(q, desc->flags & (DAS_MC_VOTES | DAS_MC_PROBS), nw, st);
     if (rc != DAS_OK) return rc;
     return reduce_partials(desc, q.fin, image_scores, st);
 }

@@ -163,27 +163,29 @@ int launch_score_tma(const McTmaParams& p, int flags, int ctas_per_sm, cudaStrea
     return DAS_OK;
 }
 
-template <int C>
-int launch_score_up(const McUpParams& p, int flags, int ctas_per_sm, cudaStream_t st) {
+// NW consumer warps per CTA (tile = 16 rows x 4 NW columns): 4 -> 3 CTAs/SM x 160 threads (2 above 24 classes),
+// 15 -> 1 CTA x 512 threads; both leave 4 warps per scheduler, i.e. 128 registers per thread (a 17th warp would
+// put 5 warps on one scheduler and cap the kernel at 96 registers).
+template <int C, int NW, int MINB>
+int launch_score_up_nw(const McUpParams& p, int flags, cudaStream_t st) {
     const bool probs = flags & DAS_MC_PROBS, votes = flags & DAS_MC_VOTES;
-    if (ctas_per_sm <= 0) ctas_per_sm = up_ctas_per_sm(C);
-    // ring depth: the windows are small (C * 144 bytes), 4 stages keep one producer round trip ahead of the consumers
+    // ring depth: the windows are small, 4 stages keep the producer one round trip ahead of the consumers
     McUpParams q = p;
     q.stages = 4;
-    const size_t smem = up_rows_bytes(C) + (size_t)q.stages * up_stage_bytes(C);
+    const size_t smem = up_rows_bytes(C, NW) + up_wts_bytes(NW) + (size_t)q.stages * up_stage_bytes(C, NW);
     const int tiles = p.B * p.tiles_x * p.tiles_y;
 #define DAS_UP(P, Q)                                                                               \
     do {                                                                                           \
-        int rc__ = set_smem(mc_score_up_kernel<C, P, Q>, smem);                                    \
+        int rc__ = set_smem(mc_score_up_kernel<C, P, Q, NW, MINB>, smem);                          \
         if (rc__ != DAS_OK) return rc__;                                                           \
         int occ__ = 0;                                                                             \
         cudaError_t e__ = cudaOccupancyMaxActiveBlocksPerMultiprocessor(                           \
-            &occ__, mc_score_up_kernel<C, P, Q>, kUpThreads, smem);                                \
+            &occ__, mc_score_up_kernel<C, P, Q, NW, MINB>, up_threads(NW), smem);                  \
         if (e__ != cudaSuccess) return cuda_fail(e__);                                             \
         if (occ__ < 1) return DAS_ERR_UNSUPPORTED;                                                 \
-        if (occ__ > ctas_per_sm) occ__ = ctas_per_sm;                                              \
+        if (occ__ > MINB) occ__ = MINB;                                                            \
         const int grid__ = tiles < kNumSMs * occ__ ? tiles : kNumSMs * occ__;                      \
-        DAS_LAUNCH((mc_score_up_kernel<C, P, Q>), grid__, kUpThreads, smem, st, q);                \
+        DAS_LAUNCH((mc_score_up_kernel<C, P, Q, NW, MINB>), grid__, up_threads(NW), smem, st, q);  \
     } while (0)
     if (probs && votes) DAS_UP(true, true);
     else if (probs) DAS_UP(true, false);
@@ -191,6 +193,15 @@ int launch_score_up(const McUpParams& p, int flags, int ctas_per_sm, cudaStream_
 #undef DAS_UP
     DAS_CHECK_LAUNCH();
     return DAS_OK;
+}
+
+template <int C>
+int launch_score_up(const McUpParams& p, int flags, int nw, cudaStream_t st) {
+    switch (nw) {
+        case 4: return launch_score_up_nw<C, 4, (C <= 24 ? 3 : 2)>(p, flags, st);
+        case 15: return launch_score_up_nw<C, 15, 1>(p, flags, st);
+        default: return DAS_ERR_INVALID_ARG;
+    }
 }
 
 template <int C>

@@ -166,18 +166,36 @@ __device__ __forceinline__ uint32_t mc_pass(const float* __restrict__ xp, uint32
 // the arithmetic of one pass on the C x VEC logits already in registers (shared by the LDG and the TMA kernels)
 template <int C, int VEC, bool PROBS, bool VOTES, bool SMEM>
 __device__ __forceinline__ uint32_t mc_pass_math(float (&x)[C][VEC], Acc<C, VEC, SMEM>& acc, float* ent) {
+    // Latency matters as much as instruction count here (3-4 warps per scheduler): the maximum is a 3-ary tree
+    // (depth 3 instead of a 18-long chain; max is exact, so the result is unchanged), the vote scan runs as two
+    // half chains, and the softmax denominator / entropy sums as 4 / 2 interleaved partial sums.
     uint32_t vote_word = 0;
     float inv[VEC];
     float m[VEC];
 #pragma unroll
     for (int j = 0; j < VEC; ++j) {
-        m[j] = x[0][j];
+        float t[C];
 #pragma unroll
-        for (int c = 1; c < C; ++c) m[j] = fmaxf(m[j], x[c][j]);
+        for (int c = 0; c < C; ++c) t[c] = x[c][j];
+#pragma unroll
+        for (int n = C; n > 1; n = (n + 2) / 3) {
+#pragma unroll
+            for (int i = 0; i < (n + 2) / 3; ++i) {
+                float v = t[3 * i];
+                if (3 * i + 1 < n) v = fmaxf(v, t[3 * i + 1]);
+                if (3 * i + 2 < n) v = fmaxf(v, t[3 * i + 2]);
+                t[i] = v;
+            }
+        }
+        m[j] = t[0];
         if (VOTES) {
-            int v = 0;
+            constexpr int HALF = (C + 1) / 2;
+            int lo = 255, hi = HALF;  // first max wins: scan each half from its last class down
 #pragma unroll
-            for (int c = C - 1; c >= 0; --c) v = (x[c][j] == m[j]) ? c : v;  // first max wins
+            for (int c = HALF - 1; c >= 0; --c) lo = (x[c][j] == m[j]) ? c : lo;
+#pragma unroll
+            for (int c = C - 1; c >= HALF; --c) hi = (x[c][j] == m[j]) ? c : hi;
+            const int v = lo != 255 ? lo : hi;
             vote_word |= (uint32_t)v << (8 * j);
         }
     }
@@ -189,20 +207,21 @@ __device__ __forceinline__ uint32_t mc_pass_math(float (&x)[C][VEC], Acc<C, VEC,
                 const int j0 = 2 * h, j1 = 2 * h + 1;
                 const f32x2 L2 = {kLog2e, kLog2e};
                 const f32x2 nmL = {-(m[j0] * kLog2e), -(m[j1] * kLog2e)};
-                f32x2 s = {0.f, 0.f}, a = {0.f, 0.f};
+                f32x2 sp[4] = {{0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}}, ap[2] = {{0.f, 0.f}, {0.f, 0.f}};
 #pragma unroll
                 for (int c = 0; c < C; ++c) {
                     const f32x2 y = fma2(f32x2{x[c][j0], x[c][j1]}, L2, nmL);
                     const f32x2 e = {ex2_approx(y.x), ex2_approx(y.y)};
-                    s = add2(s, e);
-                    a = fma2(e, y, a);
+                    sp[c & 3] = add2(sp[c & 3], e);
+                    ap[c & 1] = fma2(e, y, ap[c & 1]);
                     x[c][j0] = e.x;
                     x[c][j1] = e.y;
                 }
+                const f32x2 s = add2(add2(sp[0], sp[1]), add2(sp[2], sp[3])), a = add2(ap[0], ap[1]);
                 inv[j0] = rcp_approx(s.x);  // s in [1, C]: 1 ulp, no denormal slow path
                 inv[j1] = rcp_approx(s.y);
-                ent[j0] += log2f(s.x) - a.x * inv[j0];
-                ent[j1] += log2f(s.y) - a.y * inv[j1];
+                ent[j0] += lg2_approx(s.x) - a.x * inv[j0];
+                ent[j1] += lg2_approx(s.y) - a.y * inv[j1];
             }
 #pragma unroll
             for (int c = 0; c < C; ++c) {
@@ -221,17 +240,18 @@ __device__ __forceinline__ uint32_t mc_pass_math(float (&x)[C][VEC], Acc<C, VEC,
 #pragma unroll
             for (int j = 0; j < VEC; ++j) {
                 const float mL = m[j] * kLog2e;
-                float s = 0.f, a = 0.f;
+                float sp[4] = {0.f, 0.f, 0.f, 0.f}, ap[2] = {0.f, 0.f};  // same association as the packed path
 #pragma unroll
                 for (int c = 0; c < C; ++c) {
                     const float y = fmaf(x[c][j], kLog2e, -mL);
                     const float e = ex2_approx(y);
-                    s += e;
-                    a = fmaf(e, y, a);
+                    sp[c & 3] += e;
+                    ap[c & 1] = fmaf(e, y, ap[c & 1]);
                     x[c][j] = e;
                 }
+                const float s = (sp[0] + sp[1]) + (sp[2] + sp[3]), a = ap[0] + ap[1];
                 inv[j] = rcp_approx(s);
-                ent[j] += log2f(s) - a * inv[j];
+                ent[j] += lg2_approx(s) - a * inv[j];
             }
 #pragma unroll
             for (int c = 0; c < C; ++c) {

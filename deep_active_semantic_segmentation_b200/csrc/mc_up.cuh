@@ -24,13 +24,20 @@
 
 namespace das {
 
-constexpr int kUpTile = 16;                 // output tile edge
-constexpr int kUpRows = 6;                  // source rows / columns a tile may touch (host-checked per shape)
-constexpr int kUpCols = 6;                  // row stride of the staged window (floats): stride 6 keeps the
-                                            // phase-1 reads of 16 (class,row) items x 2 columns on 32 distinct banks
-constexpr int kUpStrip = 4;                 // columns per consumer warp
-constexpr int kUpThreads = 160;             // 4 consumer warps + 1 producer warp
+constexpr int kUpTileH = 16;                // output rows per tile
+constexpr int kUpStrip = 4;                 // output columns per consumer warp
+constexpr int kUpRows = 6;                  // source rows a tile may touch (host-checked per shape)
+constexpr int kUpClassStride = 32;          // floats between the interpolated rows of two classes: one 128-byte line per
+                                            // class, so the phase-2 LDS.64 of a warp is a single wavefront
 constexpr int kUpMaxStages = 8;
+// NW consumer warps per CTA -> tile of 16 rows x 4 NW columns; source window of 6 rows x (NW + 2) columns
+__host__ __device__ constexpr int up_tile_w(int NW) { return kUpStrip * NW; }
+__host__ __device__ constexpr int up_win_cols(int NW) { return NW + 2; }
+__host__ __device__ constexpr int up_win_stride(int NW) { return (NW + 2) | 1; }  // odd: 32 consecutive (class,row) items hit 32 banks
+constexpr int up_threads(int NW) { return 32 * (NW + 1); }
+constexpr size_t up_stage_bytes(int C, int NW) { return (size_t)C * kUpRows * up_win_stride(NW) * sizeof(float); }
+constexpr size_t up_rows_bytes(int C, int NW) { return (size_t)NW * C * kUpClassStride * sizeof(float); }
+constexpr size_t up_wts_bytes(int NW) { return (size_t)NW * 12 * sizeof(float); }
 
 struct McUpParams {
     const float* lowres[DAS_MAX_PASS_GROUP];  // [B,C,h,w] per pass
@@ -40,11 +47,7 @@ struct McUpParams {
     float rh, rw;                             // float(h-1)/float(H-1), float(w-1)/float(W-1)  (0 when H / W == 1)
 };
 
-constexpr int up_ctas_per_sm(int C) { return C <= 24 ? 3 : 2; }
-constexpr size_t up_stage_bytes(int C) { return (size_t)C * kUpRows * kUpCols * sizeof(float); }
-constexpr size_t up_rows_bytes(int C) { return (size_t)C * kUpRows * kUpTile * sizeof(float); }
-
-// ATen: source index and the weight of the upper neighbour for destination index d (align_corners=True)
+// ATen: source index and the weights of the two neighbours for destination index d (align_corners=True)
 __device__ __forceinline__ void up_source(float scale, int d, int n_in, int& i0, int& step, float& l0, float& l1) {
     const float src = __fmul_rn(scale, (float)d);
     i0 = min((int)src, n_in - 1);
@@ -53,14 +56,19 @@ __device__ __forceinline__ void up_source(float scale, int d, int n_in, int& i0,
     step = i0 < n_in - 1 ? 1 : 0;
 }
 
-template <int C, bool PROBS, bool VOTES>
-__global__ void __launch_bounds__(kUpThreads, up_ctas_per_sm(C)) mc_score_up_kernel(const __grid_constant__ McUpParams q) {
-    constexpr int NT = 128, VEC = 2;
-    constexpr int CR = C * kUpRows;                         // (class, source row) pairs per tile
-    constexpr int P1_ITERS = (CR + 15) / 16;                // phase-1 items per thread
-    constexpr uint32_t kStageBytes = (uint32_t)(C * kUpRows * kUpCols * sizeof(float));
-    constexpr uint32_t kRowsBytes = (uint32_t)(C * kUpRows * kUpTile * sizeof(float));
-    extern __shared__ __align__(16) uint8_t smem[];         // [4 warps][C][6][4] interpolated rows | ring of [C][6][6] windows
+template <int C, bool PROBS, bool VOTES, int NW, int MINB>
+__global__ void __launch_bounds__(32 * (NW + 1), MINB) mc_score_up_kernel(const __grid_constant__ McUpParams q) {
+    constexpr int NT = 32 * NW, VEC = 2;
+    constexpr int CR = C * kUpRows;                         // (class, source row) items per tile
+    constexpr int P1_ITERS = (CR + 31) / 32;                // phase-1 items per lane
+    constexpr int WC = up_win_cols(NW), WS = up_win_stride(NW), TW = up_tile_w(NW);
+    constexpr int kSlots = kUpRows * WC;                    // floats the producer copies per class
+    constexpr int SLOT_ITERS = (kSlots + 31) / 32;
+    constexpr uint32_t kStageBytes = (uint32_t)(C * kUpRows * WS * sizeof(float));
+    constexpr uint32_t kRowsBytes = (uint32_t)(NW * C * kUpClassStride * sizeof(float));
+    constexpr uint32_t kWtsBytes = (uint32_t)(NW * 12 * sizeof(float));
+    // [NW][C][32] interpolated rows | [NW][12] strip weights | ring of [C][6][WS] windows
+    extern __shared__ __align__(128) uint8_t smem[];
     __shared__ uint64_t bars[2 * kUpMaxStages];
     __shared__ uint32_t hist32[VOTES ? C * NT * VEC / 4 + 1 : 1];
     __shared__ float lut[VOTES ? 256 : 1];
@@ -70,49 +78,55 @@ __global__ void __launch_bounds__(kUpThreads, up_ctas_per_sm(C)) mc_score_up_ker
     const McFinParams& f = q.fin;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int S = q.stages, T = q.n_passes;
-    const uint32_t ring0 = tma_smem_u32(smem) + kRowsBytes, bar0 = tma_smem_u32(bars);
+    const uint32_t ring0 = tma_smem_u32(smem) + kRowsBytes + kWtsBytes, bar0 = tma_smem_u32(bars);
     const int tiles_per_image = q.tiles_x * q.tiles_y;
     const int total_tiles = q.B * tiles_per_image;
 
     if (tid == 0) {
         for (int s = 0; s < S; ++s) {
-            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar0 + 8u * s), "r"(32) : "memory");       // full
-            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar0 + 8u * (S + s)), "r"(4) : "memory");  // empty
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar0 + 8u * s), "r"(32) : "memory");        // full
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar0 + 8u * (S + s)), "r"(NW) : "memory");  // empty
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
 
-    if (warp == 4) {
-        // ===== producer warp: lane -> up to two slots (row, col) of the 6 x 6 window, one cp.async per class =====
-        constexpr int kSlots = kUpRows * kUpCols;            // 36 floats per class: slot = row * 6 + col
-        const int s0 = lane, s1 = lane + 32;
-        const bool v1 = s1 < kSlots;
+    if (warp == NW) {
+        // ===== producer warp: lane -> slots (row, col) of the 6 x WC window, one 4-byte cp.async per class and slot =====
         const size_t plane = (size_t)q.h * q.w;
+        uint32_t soff[SLOT_ITERS];  // position of the lane's slots inside a class of the staged window (floats)
+#pragma unroll
+        for (int j = 0; j < SLOT_ITERS; ++j) {
+            const int s = lane + 32 * j;
+            soff[j] = (uint32_t)((s / WC) * WS + s % WC);
+        }
         int stage = 0;
         uint32_t phase = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
             const int b = tile / tiles_per_image, t_in = tile % tiles_per_image;
-            const int ty0 = (t_in / q.tiles_x) * kUpTile, tx0 = (t_in % q.tiles_x) * kUpTile;
+            const int ty0 = (t_in / q.tiles_x) * kUpTileH, tx0 = (t_in % q.tiles_x) * TW;
             const int r_base = min((int)__fmul_rn(q.rh, (float)ty0), q.h - 1);
             const int c_base = min((int)__fmul_rn(q.rw, (float)tx0), q.w - 1);
             // clamped source coordinates: slots past the plane edge repeat the edge (never used with weight > 0)
-            const uint32_t off0 = (uint32_t)(min(r_base + s0 / kUpCols, q.h - 1) * q.w + min(c_base + s0 % kUpCols, q.w - 1));
-            const uint32_t off1 = (uint32_t)(min(r_base + s1 / kUpCols, q.h - 1) * q.w + min(c_base + s1 % kUpCols, q.w - 1));
+            uint32_t goff[SLOT_ITERS];
+#pragma unroll
+            for (int j = 0; j < SLOT_ITERS; ++j) {
+                const int s = lane + 32 * j;
+                goff[j] = (uint32_t)(min(r_base + s / WC, q.h - 1) * q.w + min(c_base + s % WC, q.w - 1));
+            }
             for (int g = 0; g < T; ++g) {
                 tma_mbar_wait(bar0 + 8u * (S + stage), phase ^ 1u);
                 const float* src = q.lowres[g] + (size_t)b * C * plane;
-                const uint32_t dst = ring0 + stage * kStageBytes;
+                uint32_t dst = ring0 + stage * kStageBytes;
 #pragma unroll 1
                 for (int c = 0; c < C; ++c) {
-                    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst + (uint32_t)(c * kSlots + s0) * 4u),
-                                 "l"(src + off0)
-                                 : "memory");
-                    if (v1)
-                        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst + (uint32_t)(c * kSlots + s1) * 4u),
-                                     "l"(src + off1)
-                                     : "memory");
+#pragma unroll
+                    for (int j = 0; j < SLOT_ITERS; ++j)
+                        if (lane + 32 * j < kSlots)
+                            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst + soff[j] * 4u), "l"(src + goff[j])
+                                         : "memory");
                     src += plane;
+                    dst += kUpRows * WS * 4u;
                 }
                 // the lane's arrival fires when all of its copies above have landed
                 asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar0 + 8u * stage) : "memory");
@@ -122,7 +136,7 @@ __global__ void __launch_bounds__(kUpThreads, up_ctas_per_sm(C)) mc_score_up_ker
         return;
     }
 
-    // ===== consumers: warp -> columns [4 warp, 4 warp + 4) of the 16 x 16 tile; lane -> pixel pair (x, x+1) of row yy =====
+    // ===== consumers: warp -> columns [4 warp, 4 warp + 4) of the tile; lane -> pixel pair (x, x+1) of row yy =====
     const SyncNamed<NT> sync;
     if (VOTES) {
         const float Tf = (float)f.T;
@@ -133,18 +147,27 @@ __global__ void __launch_bounds__(kUpThreads, up_ctas_per_sm(C)) mc_score_up_ker
         sync();
     }
     const int xp = lane & 1, yy = lane >> 1;
-    float* rows = reinterpret_cast<float*>(smem) + warp * (C * kUpRows * kUpStrip);  // warp-private
+    float* rows = reinterpret_cast<float*>(smem) + warp * (C * kUpClassStride);                 // warp-private
+    float* wts = reinterpret_cast<float*>(smem + kRowsBytes) + warp * 12;                       // warp-private
+    // phase 1: lane -> items lane, lane + 32, ... of the C * 6 (class, source row) items
+    int p1_store[P1_ITERS];
+#pragma unroll
+    for (int k = 0; k < P1_ITERS; ++k) {
+        const int i = lane + 32 * k;
+        p1_store[k] = (i / kUpRows) * kUpClassStride + (i % kUpRows) * kUpStrip;
+    }
     const bool vec_ok = (q.W & 1) == 0;  // pixel pairs are 8-byte aligned in the maps
     int stage = 0;
     uint32_t phase = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const int b = tile / tiles_per_image, t_in = tile % tiles_per_image;
-        const int ty0 = (t_in / q.tiles_x) * kUpTile, tx0 = (t_in % q.tiles_x) * kUpTile;
-        const int y = ty0 + yy, x = tx0 + kUpStrip * warp + 2 * xp;
+        const int ty0 = (t_in / q.tiles_x) * kUpTileH, tx0 = (t_in % q.tiles_x) * TW;
+        const int xs0 = tx0 + kUpStrip * warp;  // first column of this warp's strip
+        const int y = ty0 + yy, x = xs0 + 2 * xp;
         bool act[VEC];
         act[0] = y < q.H && x < q.W;
         act[1] = y < q.H && x + 1 < q.W;
-        // ---- geometry of this thread's pixels (ATen align_corners) ----
+        // ---- geometry (ATen align_corners) ----
         const int r_base = min((int)__fmul_rn(q.rh, (float)ty0), q.h - 1);
         const int c_base = min((int)__fmul_rn(q.rw, (float)tx0), q.w - 1);
         int y0, ys;
@@ -152,17 +175,29 @@ __global__ void __launch_bounds__(kUpThreads, up_ctas_per_sm(C)) mc_score_up_ker
         up_source(q.rh, min(y, q.H - 1), q.h, y0, ys, ly0, ly1);
         const int top_idx = (y0 - r_base) * kUpStrip + 2 * xp;  // float index inside the interpolated rows of class 0
         const int bot_idx = top_idx + ys * kUpStrip;
-        float lx0[VEC], lx1[VEC];
-        int a_idx[VEC], b_idx[VEC];  // the two source columns of pixel j inside (class, row) item yy (float index)
-#pragma unroll
-        for (int j = 0; j < VEC; ++j) {
-            int x0, xs;
-            up_source(q.rw, min(x + j, q.W - 1), q.w, x0, xs, lx0[j], lx1[j]);
-            a_idx[j] = yy * kUpCols + (x0 - c_base);
-            b_idx[j] = a_idx[j] + xs;
+        // the strip's 4 pixels read source columns cb, cb+1, cb+2 of the window: pixel j = W0[j] v0 + W1[j] v1 + W2[j] v2
+        // with (W0,W1,W2) = (l0,l1,0) or (0,l0,l1) - the zero weight adds an exact 0, so the value is ATen's
+        // fma(l0, a, l1*b).  The weights are warp-uniform: computed by lanes 0..3, kept in shared memory.
+        int cb;
+        {
+            int x0f, st;
+            float t0, t1;
+            up_source(q.rw, min(xs0, q.W - 1), q.w, x0f, st, t0, t1);
+            cb = x0f - c_base;
+            __syncwarp();
+            if (lane < kUpStrip) {
+                int x0;
+                up_source(q.rw, min(xs0 + lane, q.W - 1), q.w, x0, st, t0, t1);
+                const bool sh = x0 != x0f;  // this pixel starts one source column further right
+                wts[lane] = sh ? 0.f : t0;
+                wts[4 + lane] = sh ? t0 : t1;
+                wts[8 + lane] = sh ? t1 : 0.f;
+            }
+            __syncwarp();
         }
-        const f32x2 LX0 = {lx0[0], lx0[1]}, LX1 = {lx1[0], lx1[1]}, LY0 = {ly0, ly0}, LY1 = {ly1, ly1};
-        const int h_store = yy * kUpStrip + 2 * xp;
+        // never read past the window (the padding column holds garbage; columns past the plane edge repeat the edge)
+        const int i1 = min(cb + 1, WC - 1), i2 = min(cb + 2, WC - 1);
+        const f32x2 LY0 = {ly0, ly0}, LY1 = {ly1, ly1};
 
         if (VOTES) {
 #pragma unroll
@@ -178,18 +213,28 @@ __global__ void __launch_bounds__(kUpThreads, up_ctas_per_sm(C)) mc_score_up_ker
         uint32_t first_vote = 0;
 
         for (int g = 0; g < T; ++g) {
-            // ---- phase 1: horizontal interpolation of the staged window, (class, row) items yy, yy+16, ... ----
+            // ---- phase 1: horizontal interpolation of the staged window for this warp's 4 columns ----
             tma_mbar_wait(bar0 + 8u * stage, phase);
             __syncwarp();  // every lane has read the previous pass's rows
             {
-                const float* win = reinterpret_cast<const float*>(smem + kRowsBytes + stage * kStageBytes);
+                const float* win = reinterpret_cast<const float*>(smem + kRowsBytes + kWtsBytes + stage * kStageBytes) + lane * WS;
+                float v0[P1_ITERS], v1[P1_ITERS], v2[P1_ITERS];  // all loads first (the stores below may alias for the compiler)
 #pragma unroll
                 for (int k = 0; k < P1_ITERS; ++k) {
-                    if (k * 16 + yy < CR) {
-                        const float* wk = win + k * 16 * kUpCols;
-                        const f32x2 a = {wk[a_idx[0]], wk[a_idx[1]]}, bb = {wk[b_idx[0]], wk[b_idx[1]]};
-                        const f32x2 r = fma2(LX0, a, mul2(LX1, bb));
-                        *reinterpret_cast<float2*>(rows + h_store + k * 16 * kUpStrip) = make_float2(r.x, r.y);
+                    if (lane + 32 * k < CR) {
+                        const float* wk = win + k * 32 * WS;
+                        v0[k] = wk[cb], v1[k] = wk[i1], v2[k] = wk[i2];
+                    }
+                }
+                const float4 w0 = *reinterpret_cast<const float4*>(wts), w1 = *reinterpret_cast<const float4*>(wts + 4),
+                             w2 = *reinterpret_cast<const float4*>(wts + 8);
+#pragma unroll
+                for (int k = 0; k < P1_ITERS; ++k) {
+                    if (lane + 32 * k < CR) {
+                        const f32x2 V0 = {v0[k], v0[k]}, V1 = {v1[k], v1[k]}, V2 = {v2[k], v2[k]};
+                        const f32x2 lo = fma2(f32x2{w0.x, w0.y}, V0, fma2(f32x2{w1.x, w1.y}, V1, mul2(f32x2{w2.x, w2.y}, V2)));
+                        const f32x2 hi = fma2(f32x2{w0.z, w0.w}, V0, fma2(f32x2{w1.z, w1.w}, V1, mul2(f32x2{w2.z, w2.w}, V2)));
+                        *reinterpret_cast<float4*>(rows + p1_store[k]) = make_float4(lo.x, lo.y, hi.x, hi.y);
                     }
                 }
             }
@@ -197,12 +242,12 @@ __global__ void __launch_bounds__(kUpThreads, up_ctas_per_sm(C)) mc_score_up_ker
             if (lane == 0)  // this warp no longer reads the window: hand the slot back to the producer
                 asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar0 + 8u * (S + stage)) : "memory");
             if (++stage == S) stage = 0, phase ^= 1u;
-            // ---- phase 2: vertical interpolation -> the C logits of this thread's two pixels ----
+            // ---- phase 2: vertical interpolation -> the C logits of this lane's two pixels ----
             float xl[C][VEC];
 #pragma unroll
             for (int c = 0; c < C; ++c) {
-                const float2 t = *reinterpret_cast<const float2*>(rows + top_idx + c * kUpRows * kUpStrip);
-                const float2 u = *reinterpret_cast<const float2*>(rows + bot_idx + c * kUpRows * kUpStrip);
+                const float2 t = *reinterpret_cast<const float2*>(rows + top_idx + c * kUpClassStride);
+                const float2 u = *reinterpret_cast<const float2*>(rows + bot_idx + c * kUpClassStride);
                 const f32x2 v = fma2(LY0, f32x2{t.x, t.y}, mul2(LY1, f32x2{u.x, u.y}));
                 xl[c][0] = v.x, xl[c][1] = v.y;
             }
@@ -271,7 +316,7 @@ __global__ void __launch_bounds__(kUpThreads, up_ctas_per_sm(C)) mc_score_up_ker
 }
 
 template <int C>
-int launch_score_up(const McUpParams& p, int flags, int ctas_per_sm, cudaStream_t st);
-int dispatch_score_up(const McUpParams& p, int flags, int ctas_per_sm, cudaStream_t st);
+int launch_score_up(const McUpParams& p, int flags, int nw, cudaStream_t st);
+int dispatch_score_up(const McUpParams& p, int flags, int nw, cudaStream_t st);
 
 }  // namespace das

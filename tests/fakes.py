@@ -20,6 +20,20 @@ class Pool:
         return self.logits.shape[-2:]
 
 
+class LowResPool(Pool):
+    """`logits` are the decoder's low-resolution outputs [N,T,C,h,w] (models/deeplab.py:58 `low_res_x`);
+    images and labels are H x W.  A ReplayModel on this pool returns the low-resolution logits as they are:
+    it plays a model whose forward stops before the final F.interpolate."""
+
+    def __init__(self, logits, labels, H, W):
+        super().__init__(logits, labels)
+        self.full_hw = (H, W)
+
+    @property
+    def hw(self):
+        return self.full_hw
+
+
 class SyntheticPathsDataset(torch.utils.data.Dataset):
     def __init__(self, env, paths, crop_size, include_labels=False):
         self.env, self.paths, self.crop_size, self.include_labels = env, paths, crop_size, include_labels

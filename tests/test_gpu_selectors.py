@@ -89,6 +89,39 @@ def test_mc_dropout_and_ceal_selectors_match_reference(name, pass_group):
         np.testing.assert_array_equal(weak[p], g["weak_labels"][j])
 
 
+@pytest.mark.parametrize("name", ["upsample_odd", "upsample_rect", "upsample_mid"])
+def test_selectors_on_low_resolution_logits_match_reference(name):
+    """the model hands over `low_res_x` (models/deeplab.py:58); the goldens are the reference
+    selectors on F.interpolate(low_res_x) (models/deeplab.py:59).  Same selector calls, same results."""
+    g, m, low, labels = G.upsample_case(name)
+    N, T, C, k, bs = m["N"], m["T"], m["C"], m["k"], m["batch_size"]
+    pool = fakes.LowResPool(low, labels, m["H"], m["W"])
+    crop = m["H"] if m["H"] == m["W"] else -1
+    _set_T(T)
+    from deep_active_semantic_segmentation_b200 import _lib
+    n0 = _lib.launch_count()
+    sel = _factory("variance", C, pool, crop, bs)
+    model = fakes.ReplayModel(pool)
+    chosen = sel.get_vote_entropy_for_images(model, _paths(N), k)
+    assert _idx(chosen) == g["ve_selected"].tolist() and not model.drop.training
+    vtol = 1e-5 if name == "upsample_rect" else ATOL      # ATen's small even-sized path rounds differently: a vote may flip
+    np.testing.assert_allclose(sel.last_scores, g["ve_scores"], rtol=RTOL, atol=vtol)
+    nb = -(-N // bs)
+    assert 2 * nb < _lib.launch_count() - n0 <= 2 * nb + 3   # ONE fused-upsample launch + one reduce per batch, then the top-k
+    ceal = _factory("ceal_entropy", C, pool, crop, bs)
+    ent_sel, ent = ceal.get_maximum_entropy_samples(fakes.ReplayModel(pool), _paths(N), k)
+    assert _idx(ent_sel) == g["ceal_entropy_selected"].tolist()
+    np.testing.assert_allclose(ent, g["ceal_entropy"], rtol=RTOL, atol=ATOL)
+    marg_sel = ceal.get_least_margin_samples(fakes.ReplayModel(pool), _paths(N), k)
+    assert _idx(marg_sel) == g["ceal_margin_selected"].tolist()
+    np.testing.assert_allclose(ceal.last_scores, g["ceal_margin"], rtol=RTOL, atol=ATOL)
+    # a factor the fused kernel does not take is interpolated by torch on the device and scored as usual
+    big = fakes.LowResPool(low, labels[:, :2 * m["h"] - 1, :2 * m["w"] - 1], 2 * m["h"] - 1, 2 * m["w"] - 1)
+    sel2 = _factory("variance", C, big, -1, bs)
+    out = sel2.get_vote_entropy_for_images(fakes.ReplayModel(big), _paths(N), k)
+    assert len(out) == min(k, N) and all(np.isfinite(sel2.last_scores))
+
+
 @pytest.mark.parametrize("name", ["region_small", "region_mid"])
 def test_region_selector_matches_reference(name):
     g = G.load(name)
