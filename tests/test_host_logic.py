@@ -187,3 +187,27 @@ def test_header_is_plain_c(tmp_path):
     header = open(os.path.join(ROOT, "include", "das_b200.h")).read()
     code = re.sub(r"/\*.*?\*/", "", header, flags=re.S)              # declarations only, comments stripped
     assert "torch" not in code and "std::" not in code and "at::" not in code and "Tensor" not in code
+
+
+def test_upsample_shape_support_is_decided_on_the_host():
+    """das_mc_upsample_supported is host-only code (no CUDA call): the window check replays the kernel's float
+    arithmetic.  DeepLab's stride-4 decoder shapes and Fast-SCNN's factor 8 are in range, factor 2 is not."""
+    from deep_active_semantic_segmentation_b200 import _lib
+    lib = _lib.load()
+    ok = lambda h, w, H, W: bool(lib.das_mc_upsample_supported(h, w, H, W))
+    assert ok(128, 256, 512, 1024) and ok(129, 129, 513, 513) and ok(17, 17, 65, 65) and ok(12, 16, 48, 64)
+    assert ok(64, 128, 512, 1024)            # models/fastscnn.py:22 (classifier at 1/8)
+    assert not ok(32, 32, 64, 64) and not ok(64, 64, 64, 64) and not ok(100, 100, 300, 300)
+    assert not ok(0, 4, 16, 16) and not ok(4, 4, 0, 16)
+    assert ok(1, 1, 16, 16) and ok(5, 5, 16, 16)
+
+
+def test_align_corners_axis_of_the_oracle():
+    from oracle import restate as R
+    for n_in, n_out in ((128, 512), (129, 513), (256, 1024), (5, 16), (1, 7), (9, 9)):
+        i0, i1, l0, l1 = R._align_corners_axis(n_in, n_out)
+        assert i0.min() == 0 and i1.max() <= n_in - 1 and ((i1 - i0 == 0) | (i1 - i0 == 1)).all()
+        assert (l0 >= 0).all() and (l1 >= 0).all() and np.allclose(l0 + l1, 1.0)
+        assert (np.diff(i0) >= 0).all()
+        if n_out > 1:
+            assert i0[-1] + (l1[-1] > 0.5) == n_in - 1   # the last output sample sits on the last input sample
