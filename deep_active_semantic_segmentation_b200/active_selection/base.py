@@ -8,10 +8,10 @@ import sys
 import types
 
 import torch
-from torch.utils.data import DataLoader
 
 from .. import constants as _own_constants
 from .. import dist, ops
+from ..prefetch import DeviceBatchLoader
 from .._lib import MAX_PASS_GROUP, SCORE_INDEX, TOPK_MAX_K, DasError
 
 # The reference selectors reach the data layer through the module attribute
@@ -70,8 +70,11 @@ class ActiveSelectionBase:
         return lo, hi
 
     def _loader(self, images, include_labels=True):
+        """Batches in dataset order, as the reference's DataLoader(..., shuffle=False, num_workers=0) yields them
+        (mc_dropout.py:131-132) - assembled in pinned memory by worker threads and copied asynchronously, so the
+        batches arrive as CUDA tensors (prefetch.py)."""
         ds = _dataset_class()(self.env, images, self.crop_size, include_labels=include_labels)
-        return DataLoader(ds, batch_size=self.dataloader_batch_size, shuffle=False, num_workers=0)
+        return DeviceBatchLoader(ds, self.dataloader_batch_size)
 
     # -- Monte-Carlo scoring of one batch --------------------------------------------------------
     def _group_size(self, T, per_pass_bytes):

@@ -1,0 +1,100 @@
+"""Batch feeder of the selectors: what stands between the caller's dataset and the scoring kernels.
+
+The reference iterates `DataLoader(PathsDataset(...), batch_size, shuffle=False, num_workers=0)` and calls
+`.cuda()` on every batch (mc_dropout.py:131-137, ceal.py:21-29, core_set.py:42-56): collate into pageable memory,
+then a synchronous staged copy - about 11 ms per batch of eight 512 x 1024 images, invisible next to T network
+forwards but ten times the scoring kernels.  `DeviceBatchLoader` keeps the iteration order and the batch boundaries
+and shortens the host side:
+
+  * the items of a batch are stacked straight into a PINNED staging buffer (`torch.stack(..., out=...)`, one of two
+    alternating slots; the staging buffers are cached for the life of the process - page-locking costs ~0.5 ms / MB),
+  * one asynchronous copy per field on a side stream; the consumer's stream waits on the copy's event; a slot is
+    reused only when the device has finished the batch that last came out of it, so assembling batch i+1 overlaps
+    the device work of batch i and the host never runs more than two batches ahead,
+  * batches come out as CUDA tensors (`.cuda()` on them is a no-op), dict fields and bare tensors alike.
+
+Everything runs on the calling thread (worker threads were measured and dropped: with an intra-op team inside each
+worker the host is oversubscribed and the thread that enqueues the GPU work stalls - `profiles/r1_loader_notes.md`).
+Datasets whose items are not tensors / arrays of one shape per field fall back to the plain DataLoader;
+`DAS_LOADER=torch` forces it.
+"""
+from __future__ import annotations
+
+import os
+
+import numpy as np
+import torch
+from torch.utils.data import DataLoader
+
+_STAGING = {}   # (field, shape, dtype, batch) -> [pinned slot 0, pinned slot 1]
+
+
+def _as_tensor(v):
+    if isinstance(v, torch.Tensor):
+        return v
+    if isinstance(v, np.ndarray):
+        return torch.from_numpy(v)
+    raise TypeError(type(v))
+
+
+def _staging(field, t, bs):
+    key = (field, tuple(t.shape), t.dtype, bs)
+    if key not in _STAGING:
+        if sum(b[0].numel() * b[0].element_size() * 2 for b in _STAGING.values()) > (2 << 30):
+            _STAGING.clear()          # shapes changed a lot: do not hoard page-locked memory
+        _STAGING[key] = [torch.empty((bs,) + tuple(t.shape), dtype=t.dtype, pin_memory=True) for _ in range(2)]
+    return _STAGING[key]
+
+
+class DeviceBatchLoader:
+    def __init__(self, dataset, batch_size: int, device=None):
+        self.dataset, self.batch_size = dataset, int(batch_size)
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+
+    def __len__(self):
+        return -(-len(self.dataset) // self.batch_size)
+
+    def _fallback(self):
+        return iter(DataLoader(self.dataset, batch_size=self.batch_size, shuffle=False, num_workers=0))
+
+    def __iter__(self):
+        n = len(self.dataset)
+        if n == 0:
+            return
+        if os.environ.get("DAS_LOADER", "") == "torch" or not torch.cuda.is_available():
+            yield from self._fallback()
+            return
+        try:
+            first = self.dataset[0]
+            fields = {k: _as_tensor(v) for k, v in first.items()} if isinstance(first, dict) else {None: _as_tensor(first)}
+        except TypeError:
+            yield from self._fallback()
+            return
+        bs = self.batch_size
+        slots = {k: _staging(k, t, bs) for k, t in fields.items()}
+        done = [None, None]     # per slot: the consumer's stream has finished the batch that last came out of it
+        side = torch.cuda.Stream(device=self.device)
+        for bi, lo in enumerate(range(0, n, bs)):
+            slot = bi & 1
+            cur = torch.cuda.current_stream(self.device)
+            if bi > 0:          # the consumer asked for the next batch: everything it enqueued for batch bi-1 is on `cur`
+                done[slot ^ 1] = torch.cuda.Event()
+                done[slot ^ 1].record(cur)
+            items = [first if j == 0 else self.dataset[j] for j in range(lo, min(lo + bs, n))]
+            m = len(items)
+            if done[slot] is not None:
+                # double buffering with back-pressure: batch bi-2 has left the host AND the device is done with it, so
+                # the host runs at most two batches ahead and the device tensors of a batch are reused, not re-allocated
+                done[slot].synchronize()
+            for k, bufs in slots.items():
+                torch.stack([_as_tensor(it[k] if k is not None else it) for it in items], out=bufs[slot][:m])
+            with torch.cuda.stream(side):
+                dev = {k: bufs[slot][:m].to(self.device, non_blocking=True) for k, bufs in slots.items()}
+                ev = torch.cuda.Event()
+                ev.record(side)
+            cur.wait_event(ev)
+            for t in dev.values():
+                t.record_stream(cur)
+            yield dev[None] if None in dev else dev
+            del dev
+        torch.cuda.current_stream(self.device).synchronize()   # the cached staging buffers may be reused by the next loader

@@ -286,3 +286,42 @@ def test_maxsubset_region_scale_properties():
         best = float(scores.min())
         assert abs(float(scores[p]) - best) <= 1e-9 * abs(best)
         md = torch.minimum(md, D[:, p])
+
+
+def test_device_batch_loader_yields_what_the_dataloader_yields():
+    """prefetch.DeviceBatchLoader: same batches, same order as DataLoader(shuffle=False) - on the device."""
+    from torch.utils.data import DataLoader
+    from deep_active_semantic_segmentation_b200.prefetch import DeviceBatchLoader
+
+    class DictSet(torch.utils.data.Dataset):
+        def __len__(self):
+            return 11
+
+        def __getitem__(self, i):
+            g = torch.Generator().manual_seed(i)
+            return {"image": torch.randn(3, 9, 7, generator=g), "label": np.full((9, 7), float(i), np.float32)}
+
+    class BareSet(DictSet):
+        def __getitem__(self, i):
+            return super().__getitem__(i)["image"]
+
+    class OddSet(DictSet):        # items the fast path does not take: falls back to the DataLoader
+        def __getitem__(self, i):
+            return {"image": torch.zeros(2), "name": f"img{i}"}
+
+    for ds, bs in ((DictSet(), 4), (DictSet(), 11), (DictSet(), 16), (BareSet(), 3)):
+        for _ in range(2):                               # second round: cached staging buffers
+            got = [({k: v.clone() for k, v in b.items()} if isinstance(b, dict) else b.clone()) for b in DeviceBatchLoader(ds, bs)]
+            want = list(DataLoader(ds, batch_size=bs, shuffle=False, num_workers=0))
+            assert len(got) == len(want) == len(DeviceBatchLoader(ds, bs))
+            for g_, w_ in zip(got, want):
+                if isinstance(w_, dict):
+                    assert set(g_) == set(w_)
+                    for k in w_:
+                        assert g_[k].is_cuda and g_[k].dtype == w_[k].dtype
+                        torch.testing.assert_close(g_[k].cpu(), w_[k], rtol=0, atol=0)
+                else:
+                    assert g_.is_cuda
+                    torch.testing.assert_close(g_.cpu(), w_, rtol=0, atol=0)
+    odd = list(DeviceBatchLoader(OddSet(), 4))
+    assert len(odd) == 3 and odd[0]["name"] == ["img0", "img1", "img2", "img3"]
