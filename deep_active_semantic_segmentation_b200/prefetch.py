@@ -6,27 +6,40 @@ then a synchronous staged copy - about 11 ms per batch of eight 512 x 1024 image
 forwards but ten times the scoring kernels.  `DeviceBatchLoader` keeps the iteration order and the batch boundaries
 and shortens the host side:
 
-  * the items of a batch are stacked straight into a PINNED staging buffer (`torch.stack(..., out=...)`, one of two
-    alternating slots; the staging buffers are cached for the life of the process - page-locking costs ~0.5 ms / MB),
+  * the items of a batch are copied straight into a PINNED staging buffer (one of two alternating slots; the
+    staging buffers are cached for the life of the process - page-locking costs ~0.5 ms / MB): `torch.stack(out=)`
+    when the calling thread has an intra-op team, otherwise (torchrun sets OMP_NUM_THREADS=1 per rank) a few copy
+    threads doing one plain memcpy per item and field,
   * one asynchronous copy per field on a side stream; the consumer's stream waits on the copy's event; a slot is
     reused only when the device has finished the batch that last came out of it, so assembling batch i+1 overlaps
     the device work of batch i and the host never runs more than two batches ahead,
   * batches come out as CUDA tensors (`.cuda()` on them is a no-op), dict fields and bare tensors alike.
 
-Everything runs on the calling thread (worker threads were measured and dropped: with an intra-op team inside each
-worker the host is oversubscribed and the thread that enqueues the GPU work stalls - `profiles/r1_loader_notes.md`).
+The dataset is only ever read on the calling thread, and nothing is assembled ahead of the consumer (threads that
+assemble whole batches ahead were measured and dropped: with an intra-op team inside each worker the host is
+oversubscribed and the thread that enqueues the GPU work stalls - `profiles/r1_loader_notes.md`).
 Datasets whose items are not tensors / arrays of one shape per field fall back to the plain DataLoader;
 `DAS_LOADER=torch` forces it.
 """
 from __future__ import annotations
 
 import os
+from concurrent.futures import ThreadPoolExecutor
 
 import numpy as np
 import torch
 from torch.utils.data import DataLoader
 
 _STAGING = {}   # (field, shape, dtype, batch) -> [pinned slot 0, pinned slot 1]
+_COPIERS = None  # process-wide copy threads (memcpy releases the GIL)
+
+
+def _copiers():
+    global _COPIERS
+    if _COPIERS is None:
+        _COPIERS = ThreadPoolExecutor(max_workers=max(1, int(os.environ.get("DAS_LOADER_COPY_THREADS", 4))),
+                                      thread_name_prefix="das-copy")
+    return _COPIERS
 
 
 def _as_tensor(v):
@@ -86,8 +99,17 @@ class DeviceBatchLoader:
                 # double buffering with back-pressure: batch bi-2 has left the host AND the device is done with it, so
                 # the host runs at most two batches ahead and the device tensors of a batch are reused, not re-allocated
                 done[slot].synchronize()
-            for k, bufs in slots.items():
-                torch.stack([_as_tensor(it[k] if k is not None else it) for it in items], out=bufs[slot][:m])
+            if torch.get_num_threads() >= 8:
+                # an intra-op team is available on this thread: one stack per field (2 ms per 67 MB batch)
+                for k, bufs in slots.items():
+                    torch.stack([_as_tensor(it[k] if k is not None else it) for it in items], out=bufs[slot][:m])
+            else:
+                # torchrun sets OMP_NUM_THREADS=1 per rank: a few copy threads, one memcpy per item and field (4.5 ms
+                # per batch instead of 8 ms for a single-threaded stack)
+                jobs = [(bufs[slot][j], _as_tensor(it[k] if k is not None else it))
+                        for k, bufs in slots.items() for j, it in enumerate(items)]
+                for _ in _copiers().map(lambda d_s: d_s[0].copy_(d_s[1]), jobs):
+                    pass
             with torch.cuda.stream(side):
                 dev = {k: bufs[slot][:m].to(self.device, non_blocking=True) for k, bufs in slots.items()}
                 ev = torch.cuda.Event()
