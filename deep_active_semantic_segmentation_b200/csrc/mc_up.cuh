@@ -4,16 +4,21 @@
 // read from HBM: the kernel reads [B,C,h,w] (16x fewer bytes at DeepLab's stride-4 decoder), so the step is no
 // longer HBM bound but issue bound, and the interpolation is organised to cost as few issue slots as possible:
 //
-//   tile      16 x 16 output pixels per CTA; each of the 4 consumer warps owns a 16-row x 4-column strip, a lane
-//             owns a horizontal pixel pair of one row (accumulators in registers, as in mc_tma.cuh)
-//   producer  one warp copies the <= 6 x 6 low-res source window of every class into a shared-memory ring
-//             (4-byte cp.async: no alignment demands, works for 129 x 129 planes) and signals an mbarrier
-//   phase 1   a warp interpolates HORIZONTALLY, once per source row, the 4 columns of its strip:
-//             rows[warp][c][r < 6][4 px] - shared by the ~4 output rows that lie between the same two source rows
-//             (7 instructions per pixel pair and source row, 6/16 of them per output pixel pair).  The strip is
+//   tile      16 output rows x 4 NW columns per CTA (NW consumer warps: 15 -> one 512-thread CTA per SM, or 4 -> three
+//             160-thread CTAs per SM for narrow outputs); each consumer warp owns a 16-row x 4-column strip, a lane a
+//             horizontal pixel pair of one row (accumulators in registers, as in mc_tma.cuh)
+//   producer  one warp copies the 6-row x (NW + 2)-column low-res source window of every class (clamped at the plane
+//             edges) into a 4-stage shared-memory ring (4-byte cp.async: no alignment demands, works for 129 x 129
+//             planes) and signals an mbarrier (cp.async.mbarrier.arrive.noinc)
+//   phase 1   one lane per (class, source row) item interpolates HORIZONTALLY the 4 columns of its warp's strip from
+//             3 window columns: out_j = W0[j] v0 + W1[j] v1 + W2[j] v2 with (W0,W1,W2) = (l0,l1,0) or (0,l0,l1) - no
+//             per-pixel selects - and stores them with one STS.128 into rows[warp][class][row][4 px] (one 128-byte
+//             line per class).  A source row is interpolated once and shared by the ~4 output rows between the same
+//             two source rows: ~10 instructions per item, 114 items per 64 pixel pairs at C = 19.  The buffer is
 //             warp-private: __syncwarp() orders the two phases, there is no CTA barrier inside the pass loop
-//   phase 2   a lane reads the two interpolated rows around its pixel pair (2 LDS.64) and interpolates
-//             VERTICALLY with packed FMUL2 + FFMA2: 3 extra instructions per class and pass over the TMA kernel
+//   phase 2   a lane reads the two interpolated rows around its pixel pair (2 LDS.64, one wavefront each) and
+//             interpolates VERTICALLY with packed FMUL2 + FFMA2: 3 extra instructions per class and pass over the
+//             TMA kernel
 //
 // Arithmetic: indices and weights exactly as ATen's align_corners path (area_pixel_compute_scale /
 // area_pixel_compute_source_index: scale = float(in-1)/float(out-1), src = scale*dst, i0 = int(src), l1 = src-i0,
