@@ -379,6 +379,9 @@ __device__ __forceinline__ void probs_scores(GetAcc get_acc, const float* ent, f
     float pe[VEC], top1[VEC], top2[VEC];
 #pragma unroll
     for (int j = 0; j < VEC; ++j) pe[j] = 0.f, top1[j] = -1.f, top2[j] = -1.f;
+    // log2 through MUFU.LG2 (relative error 2^-22 for arguments below 0.5) for every class, then the one term whose
+    // argument can lie in (0.5, 1] - the largest probability, where MUFU.LG2 only bounds the ABSOLUTE error and the
+    // term itself is tiny - is replaced by its log2f value: 1 accurate logarithm per pixel instead of C
 #pragma unroll
     for (int c = 0; c < C; ++c) {
         float a[VEC];
@@ -386,11 +389,14 @@ __device__ __forceinline__ void probs_scores(GetAcc get_acc, const float* ent, f
 #pragma unroll
         for (int j = 0; j < VEC; ++j) {
             const float pb = a[j] * invT;
-            pe[j] = pe[j] - pb * log2f(pb + kEps);
+            pe[j] = pe[j] - pb * lg2_approx(pb + kEps);
             top2[j] = fmaxf(top2[j], fminf(top1[j], pb));
             top1[j] = fmaxf(top1[j], pb);
         }
     }
+#pragma unroll
+    for (int j = 0; j < VEC; ++j)
+        pe[j] = (pe[j] + top1[j] * lg2_approx(top1[j] + kEps)) - top1[j] * log2f(top1[j] + kEps);
 #pragma unroll
     for (int j = 0; j < VEC; ++j) {
         const float ee = ent[j] * invT;
