@@ -144,7 +144,7 @@ constexpr size_t acc_smem_bytes(int C, int VEC) { return (size_t)C * kAccThreads
 // One Monte-Carlo pass for the VEC pixels of a thread: loads the C logits of each pixel once (streaming, evict
 // first), returns the votes packed one byte per pixel and updates the running accumulators.
 //   vote   v   = first argmax_c x_c                                     (mc_dropout.py:40)
-//   softmax p_c = 2^(x_c*log2e - m*log2e) / s, s = sum_c 2^(...)        (nn.Softmax2d, ceal.py:111)
+//   softmax p_c = 2^((x_c - m)*log2e) / s, s = sum_c 2^(...)             (nn.Softmax2d, ceal.py:111)
 //   entropy of the pass: -sum p_c log2 p_c = log2 s - (sum_c e_c y_c)/s, y_c = (x_c - m) log2e <= 0
 //     (log-sum-exp form of ceal.py:118: one log2 per pixel instead of one per logit; it differs from
 //      the reference's "+1e-12" form by < 2e-12 per class and has no cancellation, both terms >= 0)
@@ -167,8 +167,8 @@ __device__ __forceinline__ uint32_t mc_pass(const float* __restrict__ xp, uint32
 template <int C, int VEC, bool PROBS, bool VOTES, bool SMEM>
 __device__ __forceinline__ uint32_t mc_pass_math(float (&x)[C][VEC], Acc<C, VEC, SMEM>& acc, float* ent) {
     // Latency matters as much as instruction count here (3-4 warps per scheduler): the maximum is a 3-ary tree
-    // (depth 3 instead of a 18-long chain; max is exact, so the result is unchanged), the vote scan runs as two
-    // half chains, and the softmax denominator / entropy sums as 4 / 2 interleaved partial sums.
+    // (depth 3 instead of a 18-long chain; max is exact, so the result is unchanged), the vote flags are collected
+    // by two half chains, and the softmax denominator / entropy sums run as 4 / 2 interleaved partial sums.
     uint32_t vote_word = 0;
     float inv[VEC];
     float m[VEC];
@@ -188,14 +188,39 @@ __device__ __forceinline__ uint32_t mc_pass_math(float (&x)[C][VEC], Acc<C, VEC,
             }
         }
         m[j] = t[0];
-        if (VOTES) {
+    }
+    // d_c = x_c - m: exactly +0 for the maxima, negative otherwise (IEEE subtraction of distinct floats is never 0),
+    // so the sign bits ARE the "not a maximum" flags: one funnel shift per class collects them (instead of a
+    // compare + select), the first maximum is the highest clear bit.  The softmax reuses d: y = d * log2(e).
+    if constexpr (VEC % 2 == 0) {
+#pragma unroll
+        for (int h = 0; h < VEC / 2; ++h) {
+            const int j0 = 2 * h, j1 = 2 * h + 1;
+            const f32x2 nm = {-m[j0], -m[j1]};
+#pragma unroll
+            for (int c = 0; c < C; ++c) {
+                const f32x2 d = add2(f32x2{x[c][j0], x[c][j1]}, nm);
+                x[c][j0] = d.x, x[c][j1] = d.y;
+            }
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < VEC; ++j)
+#pragma unroll
+            for (int c = 0; c < C; ++c) x[c][j] = x[c][j] - m[j];
+    }
+    if (VOTES) {
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) {
+            uint32_t lo = 0, hi = 0;  // two half chains; bit (n - 1 - i) of a chain = flag of its i-th class
             constexpr int HALF = (C + 1) / 2;
-            int lo = 255, hi = HALF;  // first max wins: scan each half from its last class down
 #pragma unroll
-            for (int c = HALF - 1; c >= 0; --c) lo = (x[c][j] == m[j]) ? c : lo;
+            for (int c = 0; c < HALF; ++c) lo = __funnelshift_l(__float_as_uint(x[c][j]), lo, 1);
 #pragma unroll
-            for (int c = C - 1; c >= HALF; --c) hi = (x[c][j] == m[j]) ? c : hi;
-            const int v = lo != 255 ? lo : hi;
+            for (int c = HALF; c < C; ++c) hi = __funnelshift_l(__float_as_uint(x[c][j]), hi, 1);
+            const uint32_t notmax = (lo << (C - HALF)) | hi;                   // bit (C - 1 - c) = flag of class c
+            const uint32_t ismax = ~notmax & (0xffffffffu >> (32 - C));
+            const int v = __clz(ismax) - (32 - C);                            // first maximum = highest set bit
             vote_word |= (uint32_t)v << (8 * j);
         }
     }
@@ -206,11 +231,10 @@ __device__ __forceinline__ uint32_t mc_pass_math(float (&x)[C][VEC], Acc<C, VEC,
             for (int h = 0; h < VEC / 2; ++h) {
                 const int j0 = 2 * h, j1 = 2 * h + 1;
                 const f32x2 L2 = {kLog2e, kLog2e};
-                const f32x2 nmL = {-(m[j0] * kLog2e), -(m[j1] * kLog2e)};
                 f32x2 sp[4] = {{0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}}, ap[2] = {{0.f, 0.f}, {0.f, 0.f}};
 #pragma unroll
                 for (int c = 0; c < C; ++c) {
-                    const f32x2 y = fma2(f32x2{x[c][j0], x[c][j1]}, L2, nmL);
+                    const f32x2 y = mul2(f32x2{x[c][j0], x[c][j1]}, L2);
                     const f32x2 e = {ex2_approx(y.x), ex2_approx(y.y)};
                     sp[c & 3] = add2(sp[c & 3], e);
                     ap[c & 1] = fma2(e, y, ap[c & 1]);
@@ -239,11 +263,10 @@ __device__ __forceinline__ uint32_t mc_pass_math(float (&x)[C][VEC], Acc<C, VEC,
         } else {
 #pragma unroll
             for (int j = 0; j < VEC; ++j) {
-                const float mL = m[j] * kLog2e;
                 float sp[4] = {0.f, 0.f, 0.f, 0.f}, ap[2] = {0.f, 0.f};  // same association as the packed path
 #pragma unroll
                 for (int c = 0; c < C; ++c) {
-                    const float y = fmaf(x[c][j], kLog2e, -mL);
+                    const float y = x[c][j] * kLog2e;
                     const float e = ex2_approx(y);
                     sp[c & 3] += e;
                     ap[c & 1] = fmaf(e, y, ap[c & 1]);
