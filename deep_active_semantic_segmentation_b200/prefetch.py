@@ -10,10 +10,14 @@ and shortens the host side:
     staging buffers are cached for the life of the process - page-locking costs ~0.5 ms / MB): `torch.stack(out=)`
     when the calling thread has an intra-op team, otherwise (torchrun sets OMP_NUM_THREADS=1 per rank) a few copy
     threads doing one plain memcpy per item and field,
-  * one asynchronous copy per field on a side stream; the consumer's stream waits on the copy's event; a slot is
-    reused only when the device has finished the batch that last came out of it, so assembling batch i+1 overlaps
-    the device work of batch i and the host never runs more than two batches ahead,
-  * batches come out as CUDA tensors (`.cuda()` on them is a no-op), dict fields and bare tensors alike.
+  * one asynchronous copy per field on a side stream into one of two DEVICE slots (cached as well: a fresh
+    allocation on a side stream goes through cudaMalloc / cudaFree of the caching allocator and stalled single
+    calls by 100-200 ms); the consumer's stream waits on the copy's event; a slot pair is reused only when the device
+    has finished the batch that last came out of it, so assembling batch i+1 overlaps the device work of batch i and
+    the host never runs more than two batches ahead,
+  * batches come out as CUDA tensors (`.cuda()` on them is a no-op), dict fields and bare tensors alike.  A batch is
+    a view of a device slot: it stays valid until the loader has been asked for two more batches (the selectors
+    consume a batch before they ask for the next one).
 
 The dataset is only ever read on the calling thread, and nothing is assembled ahead of the consumer (threads that
 assemble whole batches ahead were measured and dropped: with an intra-op team inside each worker the host is
@@ -30,7 +34,8 @@ import numpy as np
 import torch
 from torch.utils.data import DataLoader
 
-_STAGING = {}   # (field, shape, dtype, batch) -> [pinned slot 0, pinned slot 1]
+_STAGING = {}   # (device, field, shape, dtype, batch) -> ([pinned slot 0, pinned slot 1], [device slot 0, device slot 1])
+_SIDE = {}      # device -> copy stream
 _COPIERS = None  # process-wide copy threads (memcpy releases the GIL)
 
 
@@ -50,13 +55,23 @@ def _as_tensor(v):
     raise TypeError(type(v))
 
 
-def _staging(field, t, bs):
-    key = (field, tuple(t.shape), t.dtype, bs)
+def _staging(device, field, t, bs):
+    key = (str(device), field, tuple(t.shape), t.dtype, bs)
     if key not in _STAGING:
-        if sum(b[0].numel() * b[0].element_size() * 2 for b in _STAGING.values()) > (2 << 30):
-            _STAGING.clear()          # shapes changed a lot: do not hoard page-locked memory
-        _STAGING[key] = [torch.empty((bs,) + tuple(t.shape), dtype=t.dtype, pin_memory=True) for _ in range(2)]
+        if sum(h[0].numel() * h[0].element_size() * 2 for h, _ in _STAGING.values()) > (2 << 30):
+            torch.cuda.synchronize()
+            _STAGING.clear()          # shapes changed a lot: do not hoard page-locked / device memory
+        shape = (bs,) + tuple(t.shape)
+        _STAGING[key] = ([torch.empty(shape, dtype=t.dtype, pin_memory=True) for _ in range(2)],
+                         [torch.empty(shape, dtype=t.dtype, device=device) for _ in range(2)])
     return _STAGING[key]
+
+
+def _side_stream(device):
+    key = str(device)
+    if key not in _SIDE:
+        _SIDE[key] = torch.cuda.Stream(device=device)
+    return _SIDE[key]
 
 
 class DeviceBatchLoader:
@@ -84,9 +99,10 @@ class DeviceBatchLoader:
             yield from self._fallback()
             return
         bs = self.batch_size
-        slots = {k: _staging(k, t, bs) for k, t in fields.items()}
+        slots = {k: _staging(self.device, k, t, bs) for k, t in fields.items()}     # field -> (pinned pair, device pair)
         done = [None, None]     # per slot: the consumer's stream has finished the batch that last came out of it
-        side = torch.cuda.Stream(device=self.device)
+        side = _side_stream(self.device)
+        torch.cuda.current_stream(self.device).synchronize()   # an abandoned earlier loader may still own the slots
         for bi, lo in enumerate(range(0, n, bs)):
             slot = bi & 1
             cur = torch.cuda.current_stream(self.device)
@@ -101,22 +117,20 @@ class DeviceBatchLoader:
                 done[slot].synchronize()
             if torch.get_num_threads() >= 8:
                 # an intra-op team is available on this thread: one stack per field (2 ms per 67 MB batch)
-                for k, bufs in slots.items():
-                    torch.stack([_as_tensor(it[k] if k is not None else it) for it in items], out=bufs[slot][:m])
+                for k, (pinned, _) in slots.items():
+                    torch.stack([_as_tensor(it[k] if k is not None else it) for it in items], out=pinned[slot][:m])
             else:
                 # torchrun sets OMP_NUM_THREADS=1 per rank: a few copy threads, one memcpy per item and field (4.5 ms
                 # per batch instead of 8 ms for a single-threaded stack)
-                jobs = [(bufs[slot][j], _as_tensor(it[k] if k is not None else it))
-                        for k, bufs in slots.items() for j, it in enumerate(items)]
+                jobs = [(pinned[slot][j], _as_tensor(it[k] if k is not None else it))
+                        for k, (pinned, _) in slots.items() for j, it in enumerate(items)]
                 for _ in _copiers().map(lambda d_s: d_s[0].copy_(d_s[1]), jobs):
                     pass
             with torch.cuda.stream(side):
-                dev = {k: bufs[slot][:m].to(self.device, non_blocking=True) for k, bufs in slots.items()}
+                dev = {k: device_[slot][:m].copy_(pinned[slot][:m], non_blocking=True) for k, (pinned, device_) in slots.items()}
                 ev = torch.cuda.Event()
                 ev.record(side)
             cur.wait_event(ev)
-            for t in dev.values():
-                t.record_stream(cur)
             yield dev[None] if None in dev else dev
             del dev
         torch.cuda.current_stream(self.device).synchronize()   # the cached staging buffers may be reused by the next loader
