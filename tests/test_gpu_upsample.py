@@ -107,6 +107,8 @@ CASES = [
     (1, 4, 32, 9, 9, 40, 40),          # maximum class count (2 CTAs / SM configuration)
     (2, 6, 11, 6, 7, 41, 47),          # factor ~8 (models/fastscnn.py:22 upsamples its 1/8 classifier output)
     (1, 32, 19, 12, 12, 48, 48),       # maximum passes per launch
+    (1, 3, 32, 33, 33, 129, 129),      # wide output -> the 15-warp CTA (16 x 60 tiles), maximum class count
+    (2, 2, 2, 9, 61, 33, 241),         # 15-warp CTA with two classes; 241 = 4 * 60 + 1: a tile with one active column
 ]
 
 
