@@ -211,3 +211,21 @@ def test_align_corners_axis_of_the_oracle():
         assert (np.diff(i0) >= 0).all()
         if n_out > 1:
             assert i0[-1] + (l1[-1] > 0.5) == n_in - 1   # the last output sample sits on the last input sample
+
+
+def test_batch_feeder_falls_back_to_the_dataloader_without_cuda(monkeypatch):
+    """prefetch.DeviceBatchLoader on a box without a GPU (or with DAS_LOADER=torch) is the reference's DataLoader loop"""
+    from deep_active_semantic_segmentation_b200.prefetch import DeviceBatchLoader
+
+    class DS(torch.utils.data.Dataset):
+        def __len__(self):
+            return 5
+
+        def __getitem__(self, i):
+            return {"image": torch.full((3, 4, 4), float(i)), "label": torch.full((4, 4), float(-i))}
+
+    monkeypatch.setenv("DAS_LOADER", "torch")
+    batches = list(DeviceBatchLoader(DS(), 2, device="cpu"))
+    assert [b["image"].shape[0] for b in batches] == [2, 2, 1] and len(DeviceBatchLoader(DS(), 2, device="cpu")) == 3
+    assert float(batches[2]["label"][0, 0, 0]) == -4.0 and not batches[0]["image"].is_cuda
+    assert list(DeviceBatchLoader(torch.utils.data.TensorDataset(torch.zeros(0, 1)), 2, device="cpu")) == []
