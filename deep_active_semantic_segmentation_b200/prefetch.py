@@ -77,7 +77,9 @@ def _side_stream(device):
 class DeviceBatchLoader:
     def __init__(self, dataset, batch_size: int, device=None):
         self.dataset, self.batch_size = dataset, int(batch_size)
-        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        if device is None:
+            device = torch.device("cuda", torch.cuda.current_device()) if torch.cuda.is_available() else "cpu"
+        self.device = torch.device(device)
 
     def __len__(self):
         return -(-len(self.dataset) // self.batch_size)
@@ -89,7 +91,7 @@ class DeviceBatchLoader:
         n = len(self.dataset)
         if n == 0:
             return
-        if os.environ.get("DAS_LOADER", "") == "torch" or not torch.cuda.is_available():
+        if os.environ.get("DAS_LOADER", "") == "torch" or self.device.type != "cuda":
             yield from self._fallback()
             return
         try:
