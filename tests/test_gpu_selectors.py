@@ -325,3 +325,21 @@ def test_device_batch_loader_yields_what_the_dataloader_yields():
                     torch.testing.assert_close(g_.cpu(), w_, rtol=0, atol=0)
     odd = list(DeviceBatchLoader(OddSet(), 4))
     assert len(odd) == 3 and odd[0]["name"] == ["img0", "img1", "img2", "img3"]
+
+
+def test_region_selector_on_low_resolution_logits_equals_full_resolution():
+    """create_region_maps with a model that returns low_res_x == create_region_maps on F.interpolate(low_res_x)
+    (ATen on the CPU, which the fused kernel reproduces bit for bit at this shape: 17 -> 65)."""
+    from deep_active_semantic_segmentation_b200 import synth
+    N, T, C, h, H, R, bs = 5, 4, 19, 17, 65, 17, 2
+    low = synth.pool_logits(31, list(range(N)), T, C, h, h, 2)
+    labels = synth.pool_labels(31, list(range(N)), H, H, C, 8)
+    full = torch.nn.functional.interpolate(torch.from_numpy(low).reshape(N * T, C, h, h), size=(H, H), mode="bilinear",
+                                           align_corners=True).reshape(N, T, C, H, H).numpy()
+    existing = [[], [(3, 5, R, R)], [], [(0, 0, H, H)], [(20, 30, R, R), (40, 2, R, R)]]
+    _set_T(T)
+    out = []
+    for pool in (fakes.LowResPool(low, labels, H, H), fakes.Pool(full, labels)):
+        sel = _factory("variance", C, pool, H, bs)
+        out.append(sel.create_region_maps(fakes.ReplayModel(pool), _paths(N), existing, R, 2))
+    assert out[0] == out[1] and out[0][1] > 0
