@@ -12,7 +12,7 @@ import torch
 from .. import constants as _own_constants
 from .. import dist, ops
 from ..prefetch import DeviceBatchLoader
-from .._lib import MAX_PASS_GROUP, SCORE_INDEX, TOPK_MAX_K, DasError
+from .._lib import MAX_PASS_GROUP, TOPK_MAX_K, DasError
 
 # The reference selectors reach the data layer through the module attribute
 # `paths_dataset.PathsDataset` (mc_dropout.py:131, ceal.py:21, core_set.py:42).  The data layer is out

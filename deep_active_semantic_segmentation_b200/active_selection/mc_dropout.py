@@ -13,7 +13,7 @@ import random
 
 import torch
 
-from .. import dist, ops
+from .. import ops
 from .._lib import SCORE_INDEX
 from . import base
 from .base import ActiveSelectionBase, mc_steps, turn_on_dropout

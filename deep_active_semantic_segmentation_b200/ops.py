@@ -13,7 +13,7 @@ from typing import Iterable, Sequence
 import torch
 
 from . import _lib
-from ._lib import MC_PROBS, MC_SINGLE_SHOT, MC_VOTES, N_SCORES, SCORE_INDEX, DasError, McDesc, check
+from ._lib import MC_PROBS, MC_SINGLE_SHOT, MC_VOTES, N_SCORES, DasError, McDesc, check
 
 MAP_NAMES = ("vote_entropy", "pred_entropy", "bald", "confidence", "margin")
 
