@@ -204,12 +204,9 @@ def run_b200(args):
                 (fin_events if last else acc_events).append((e0, e1, len(grp)))
 
     def select():
+        # K3 on the shard -> candidate records -> ONE all-gather -> K3 merge on every rank -> one D2H of the winners
         col = pool_scores[:, SCORE_INDEX["bald" if probs else "vote_entropy"]].contiguous()
-        s, i = ops.topk(col, min(TOPK, col.numel()), True)
-        if world > 1:
-            cs, ci = dist.gather_candidates(s, i + rank * K * B, TOPK)
-            return dist.merge_ranked(cs, ci, TOPK, True)[1]
-        return i
+        return dist.select_ranked(col, min(TOPK, world * col.numel()), True, id_offset=rank * K * B)[1]
 
     sampler = ClockSampler(local) if rank == 0 else None
     for i in range(Wm):
@@ -242,7 +239,7 @@ def run_b200(args):
     alg_bytes = sum(k_bytes) / len(k_bytes)
     peaks, peak_kind = measured_peaks()
     achieved = sum(k_bytes) / (sum(k_ms) * 1e-3) / 1e9
-    tma = G >= T and os.environ.get("DAS_MC_TMA", "1")[:1] != "0"
+    tma = G >= T and _lib.get_option("mc_tma") == 1
     traffic = None
     tf = os.path.join(ROOT, "profiles", "k1_traffic.json")
     if os.path.exists(tf):
@@ -287,7 +284,7 @@ def run_b200(args):
                        "l2": f"inputs {T * B * C * H * W * 4 / 1e9:.2f} GB per step >> 126 MB L2 (no flush needed)"},
             "roofline": roofline, "cpu_baseline": cpu, "torch_gpu_baseline": torch_gpu, "e2e": e2e,
             "fused_upsample_variant": fused_up, "gpu_launches": int(launches), "clocks": clocks,
-            "selected_head": [int(v) for v in (chosen[:5].tolist() if hasattr(chosen, "tolist") else chosen[:5])],
+            "selected_head": [int(v) for v in chosen[:5].tolist()],
         }
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -125,15 +125,17 @@ class ActiveSelectionBase:
         stable global merge -> tuple of the first k paths (all ranks return the same tuple)."""
         if len(images) == 0:
             raise IndexError("list index out of range")   # the reference fails on zip(*[])[1] (mc_dropout.py:195)
-        n = local_scores.numel()
         k_eff = max(0, min(int(k), len(images)))
-        if n and k_eff:
-            s, i = ops.topk(local_scores, min(k_eff, n), descending)
-        else:
-            s, i = local_scores[:0], torch.empty(0, dtype=torch.int64, device=local_scores.device)
-        cs, ci = dist.gather_candidates(s, i + lo, max(k_eff, 1))
-        _, ids = dist.merge_ranked(cs, ci, k_eff, descending)
-        return tuple(images[j] for j in ids)
+        if k_eff == 0:
+            return ()
+        if k_eff > TOPK_MAX_K:
+            # more winners than one K3 launch ranks (the reference's sorted()[:k] has no limit): the stable sort of the
+            # gathered pool scores on the host - a selection of thousands of images out of a pool is not a hot path
+            vals = self._all_scores(local_scores, len(images))
+            order = sorted(range(len(vals)), key=vals.__getitem__, reverse=descending)[:k_eff]
+            return tuple(images[j] for j in order)
+        _, ids = dist.select_ranked(local_scores, k_eff, descending, id_offset=lo)
+        return tuple(images[int(j)] for j in ids)
 
     def _all_scores(self, local_scores, n_total):
         """Full score list in global order (list of python floats), gathered over ranks."""
@@ -196,11 +198,10 @@ def global_nms(score_maps, lo, n_images, region_size, max_selection_count, kmax)
         return dist.merge_nms_sequences(seqs, region_size, max_selection_count, H2, W2)
     if N_local > 0:
         cs, rc, cnt, flat = ops.nms_sequences(score_maps, region_size, kmax, 0.01, image_offset=lo, with_flat=True)
-        s, ids = ops.topk(cs.reshape(-1), min(want, cs.numel()), True, ids=flat.reshape(-1))
+        gs, gi = dist.select_ranked(cs.reshape(-1), max(want, 1), True, ids=flat.reshape(-1))
     else:
-        s = torch.empty(0, dtype=torch.float32, device=score_maps.device)
-        ids = torch.empty(0, dtype=torch.int64, device=score_maps.device)
-    gs, gi = dist.gather_ranked_np(s, ids, max(want, 1), True)
+        gs, gi = dist.select_ranked(torch.empty(0, dtype=torch.float32, device=score_maps.device), max(want, 1), True,
+                                    ids=torch.empty(0, dtype=torch.int64, device=score_maps.device))
     # stop rule on the merged prefix: candidates exist (id >= 0, score > -inf), at most `want` picks, and every
     # pick after the first needs score >= 0.01 (the pool maximum the reference checks after the previous pick)
     ok = (gi >= 0) & np.isfinite(gs)

@@ -3,6 +3,8 @@ average-pooled decoder features.  Feature extraction stays in PyTorch on the dev
 D2H, core_set.py:63); distances / min-update / arg-max run in the K4 kernels (fp64 accumulation)."""
 from __future__ import annotations
 
+import warnings
+
 import numpy as np
 import torch
 import torch.nn.functional as F
@@ -39,19 +41,48 @@ class ActiveSelectionCoreSet(ActiveSelectionBase):
 
     @staticmethod
     def _as_device_features(features):
+        """[n, D] numpy / tensor of any float type -> float32 CUDA tensor.  The reference's matrix is float64 but holds
+        float32 network outputs (core_set.py:50,63), which float32 carries exactly; genuinely wider values are rounded
+        to float32 with a warning (the kernels read float32 rows and accumulate in float64)."""
         if isinstance(features, torch.Tensor):
             f = features
             if f.dtype != torch.float32:
-                if not torch.equal(f.to(torch.float32).to(f.dtype), f):
-                    raise DasError("core-set features must be exactly representable in float32")
-                f = f.to(torch.float32)
+                f32 = f.to(torch.float32)
+                if not torch.equal(f32.to(f.dtype), f):
+                    warnings.warn("core-set features are not exactly representable in float32: rounded to float32 "
+                                  "(the reference stores float32 network outputs, core_set.py:50,63)", RuntimeWarning)
+                f = f32
             return f.cuda().contiguous()
         a = np.asarray(features)
         a32 = a.astype(np.float32)
         if not np.array_equal(a32.astype(np.float64), a.astype(np.float64)):
-            raise DasError("core-set features must be exactly representable in float32 "
-                           "(the reference stores float32 network outputs, core_set.py:50,63)")
+            warnings.warn("core-set features are not exactly representable in float32: rounded to float32 "
+                          "(the reference stores float32 network outputs, core_set.py:50,63)", RuntimeWarning)
         return torch.from_numpy(np.ascontiguousarray(a32)).cuda()
+
+    def _updated_distances(self, cluster_centers, features, min_distances):
+        """Same contract as core_set.py:32-38: euclidean distances (float64) of every row of `features` to the rows
+        `cluster_centers`; min over the centres as an [n, 1] column when `min_distances` is None, otherwise
+        np.minimum(min_distances, distances) (an [n, len(cluster_centers)] array, [n, 1] for the reference's only call
+        shape `[ind]`).  The distances come from the K4 init kernel (exact float32 differences accumulated in float64;
+        sklearn's expanded form differs from that in the last few ulp).  Returns numpy, like the reference."""
+        feats = self._as_device_features(features)
+        n = feats.shape[0]
+        centres = [int(c) for c in cluster_centers]
+        if len(centres) == 0:
+            raise ValueError("Found array with 0 sample(s)")       # what sklearn.pairwise_distances raises
+        dev = feats.device
+        key = torch.zeros(2, dtype=torch.int64, device=dev)
+
+        def column(cs):
+            d2 = torch.empty(n, dtype=torch.float64, device=dev)
+            ops.kcenter_init(feats, 0, n, torch.as_tensor(cs, dtype=torch.int32, device=dev), d2, key)
+            return d2.sqrt_()
+
+        if min_distances is None:
+            return column(centres).cpu().numpy().reshape(-1, 1)
+        dist_cols = torch.stack([column([c]) for c in centres], dim=1).cpu().numpy()
+        return np.minimum(np.asarray(min_distances), dist_cols)
 
     def _select_batch(self, features, selected_indices, N):
         """features [n,D] (numpy / tensor), selected_indices list[int], N picks -> list[int] (core_set.py:17-30)."""
@@ -111,22 +142,28 @@ class ActiveSelectionCoreSet(ActiveSelectionBase):
         return [int(p) for p in torch.stack(picks).cpu().tolist()] if picks else [], torch.cat(parts).sqrt()
 
     def _pooled_features(self, model, combined_paths):
+        """[len(combined_paths), D] float32 on the device.  The forwards - the real cost of this selector - are sharded
+        by image over the ranks (each rank runs the network on its contiguous slice only) and the pooled rows are
+        all-gathered; the greedy loop that follows is replicated (see `shard_rows`)."""
         name = model.module.model_name
         if name not in _POOL:
             raise NotImplementedError(name)
         ks = _POOL[name]
+        lo, hi = self._shard(combined_paths)
         rows = []
         model.eval()
         model.module.set_return_features(True)
         try:
             with torch.no_grad():
-                for sample in self._loader(combined_paths, include_labels=False):
+                for sample in self._loader(combined_paths[lo:hi], include_labels=False):
                     _, fb = model(sample.cuda())
                     fb = F.avg_pool2d(fb, ks, ks[0] // 2)
                     rows.append(fb.reshape(fb.shape[0], -1).to(torch.float32))   # channel-major flatten (core_set.py:63)
         finally:
             model.module.set_return_features(False)
-        return torch.cat(rows).contiguous()
+        local = torch.cat(rows).contiguous() if rows else torch.empty((0, 0), dtype=torch.float32, device="cuda")
+        self.last_forward_rows = hi - lo
+        return dist.all_gather_rows(local, len(combined_paths))
 
     def get_k_center_greedy_selections(self, selection_size, model, candidate_image_batch, already_selected_image_batch):
         combined_paths = already_selected_image_batch + candidate_image_batch

@@ -74,6 +74,26 @@ class ActiveSelectionMCNoise(ActiveSelectionMCDropout):
         col, lo = self._pool(images, lambda x, y: self._ve(noisy_forward, x, y, maps=False)["scores"][:, _VE])
         return self._rank(col, lo, images, selection_count, descending=True)
 
+    # ---- BASELINE config 4 (composed): CEAL entropy / margin / confidence over T input-noise passes ----
+    def get_mc_scores_for_images_with_input_noise(self, model, images, selection_count, score="pred_entropy"):
+        """The perturbation of mc_noise.py:26-27 (every pass sees image + N(0, 0.125), model in eval mode) with the
+        scores of ceal.py evaluated on the Monte-Carlo mean softmax: 'pred_entropy' (ceal.py:111-123, descending),
+        'margin' / 'confidence' (ceal.py:84-97, 36-39; ascending), plus 'bald' / 'expected_entropy' / 'vote_entropy'
+        from the same pass over the logits.  With constants.MC_STEPS = 1 and sigma -> 0 this is exactly CEAL.
+        Returns (paths, {score name: [scores of the whole pool]}), like get_mc_scores_for_images."""
+        if score not in SCORE_INDEX:
+            raise NotImplementedError(score)
+        model.eval()
+
+        def noisy_forward(x):
+            return model(x + torch.randn_like(x) * INPUT_NOISE_SIGMA)
+
+        scores, lo = self._pool_scores(model, images, mc_steps(), votes=True, probs=True, forward=noisy_forward)
+        allv = {name: self._all_scores(scores[:, j].contiguous(), len(images)) for name, j in SCORE_INDEX.items()}
+        self.last_scores = allv[score]
+        descending = score not in ("confidence", "margin")
+        return self._rank(scores[:, SCORE_INDEX[score]].contiguous(), lo, images, selection_count, descending), allv
+
     def get_vote_entropy_for_images_with_feature_noise(self, model, images, selection_count):
         model.eval()
         col, lo = self._pool(images, lambda x, y: self._feature_noise(model, x, y, maps=False)["scores"][:, _VE])

@@ -102,8 +102,9 @@ int das_accuracy_workspace_bytes(int B, int H, int W, size_t* bytes) {
     return DAS_OK;
 }
 
-int das_accuracy_scores(const float* logits, int B, int C, int H, int W, const float* labels, int num_classes,
-                        float* p0_map, float* image_scores, void* workspace, void* stream) {
+int das_accuracy_scores(das_handle* h, const float* logits, int B, int C, int H, int W, const float* labels,
+                        int num_classes, float* p0_map, float* image_scores, void* workspace, void* stream) {
+    DAS_ENTER(h);
     if (logits == nullptr || image_scores == nullptr || workspace == nullptr) return DAS_ERR_INVALID_ARG;
     if (B <= 0 || C < 1 || H <= 0 || W <= 0 || num_classes < 1) return DAS_ERR_INVALID_ARG;
     if (B > 65535) return DAS_ERR_UNSUPPORTED;

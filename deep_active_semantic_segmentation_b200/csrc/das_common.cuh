@@ -1,27 +1,89 @@
 // Shared device/host helpers for libdas_b200 (sm_100a only).
 #pragma once
 
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <atomic>
+
 #include "das_b200.h"
+
+// ---- the per-device handle (include/das_b200.h: das_handle) -----------------------------------
+// Everything that used to be process state lives here: device ordinal + SM count (grid sizing), the tuning options
+// (environment read once, at creation), the k-center step scratch table and a cache of encoded TMA descriptors.
+struct das_tmap_entry {
+    const void* base;
+    unsigned long long dims[3];
+    unsigned long long strides[2];
+    unsigned int box[3];
+    int rank, dtype, swizzle, valid;
+    CUtensorMap map;
+};
+struct das_handle {
+    unsigned int magic;
+    int device;
+    int num_sms;
+    size_t l2_bytes;            // cudaDevAttrL2CacheSize
+    size_t l2_persist_max;      // cudaDevAttrMaxPersistingL2CacheSize
+    size_t l2_window_max;       // cudaDevAttrMaxAccessPolicyWindowSize
+    size_t l2_persist_set;      // what cudaLimitPersistingL2CacheSize was last raised to by this handle
+    int opt[DAS_OPT_COUNT];
+    void* kc_step_table;        // device: KcBest[num_sms * 4], allocated on first use (das_kcenter_init / _step)
+    static constexpr int kTmapSlots = 64;
+    das_tmap_entry tmaps[kTmapSlots];
+    int tmap_next;
+    unsigned long long tmap_hits, tmap_misses;
+};
+constexpr unsigned int kDasHandleMagic = 0xDA5B200Au;
 
 namespace das {
 
 // ---- host side bookkeeping -----------------------------------------------------------------
-extern int g_last_cuda_error;
-extern unsigned long long g_launch_count;
+extern thread_local int g_last_cuda_error;
+extern std::atomic<unsigned long long> g_launch_count;
 
 inline int cuda_fail(cudaError_t e) {
     g_last_cuda_error = (int)e;
     return DAS_ERR_CUDA;
 }
 
+// Entry-point prologue: validates the handle and makes its device current for the duration of the call.
+struct HandleScope {
+    int prev = -1, rc = DAS_OK;
+    bool switched = false;
+    explicit HandleScope(const das_handle* h) {
+        if (h == nullptr || h->magic != kDasHandleMagic) {
+            rc = DAS_ERR_INVALID_ARG;
+            return;
+        }
+        cudaError_t e = cudaGetDevice(&prev);
+        if (e != cudaSuccess) {
+            rc = cuda_fail(e);
+            return;
+        }
+        if (prev != h->device) {
+            e = cudaSetDevice(h->device);
+            if (e != cudaSuccess) {
+                rc = cuda_fail(e);
+                return;
+            }
+            switched = true;
+        }
+    }
+    ~HandleScope() {
+        if (switched) cudaSetDevice(prev);
+    }
+};
+#define DAS_ENTER(h)                     \
+    ::das::HandleScope das_scope__(h);   \
+    if (das_scope__.rc != DAS_OK) return das_scope__.rc
+
 // every kernel launch goes through this so that das_launch_count() is an honest count
 #define DAS_LAUNCH(kernel, grid, block, smem, stream, ...)                 \
     do {                                                                   \
         kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__);        \
-        ++::das::g_launch_count;                                           \
+        ::das::g_launch_count.fetch_add(1, std::memory_order_relaxed);     \
     } while (0)
 
 #define DAS_CHECK_LAUNCH()                                                 \
@@ -39,7 +101,7 @@ inline int cuda_fail(cudaError_t e) {
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
-constexpr int kNumSMs = 148;  // B200: 2 dies x 74 SMs
+constexpr int kNumSMsB200 = 148;  // B200: 2 dies x 74 SMs (documentation; grids are sized from das_handle::num_sms)
 
 // state layout shared by accumulate / finalize (offsets in bytes, all 256-byte aligned)
 struct McLayout {

@@ -454,37 +454,6 @@ __global__ void __launch_bounds__(256) kc_prepare_kernel(const float* __restrict
     }
 }
 
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static EncodeTiledFn encode_tiled_fn() {
-    static EncodeTiledFn fn = nullptr;
-    if (fn == nullptr) {
-        void* p = nullptr;
-        cudaDriverEntryPointQueryResult q;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
-            q == cudaDriverEntryPointSuccess)
-            fn = reinterpret_cast<EncodeTiledFn>(p);
-    }
-    return fn;
-}
-
-int make_tensor_map(CUtensorMap* map, CUtensorMapDataType dtype, int rank, const void* base, const cuuint64_t* dims,
-                    const cuuint64_t* strides, const cuuint32_t* box, CUtensorMapSwizzle swizzle) {
-    EncodeTiledFn enc = encode_tiled_fn();
-    if (enc == nullptr) return DAS_ERR_CUDA;
-    const cuuint32_t estr[3] = {1, 1, 1};
-    const CUresult r = enc(map, dtype, (cuuint32_t)rank, const_cast<void*>(base), dims, strides, box, estr,
-                           CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) {
-        g_last_cuda_error = (int)r;
-        return DAS_ERR_CUDA;
-    }
-    return DAS_OK;
-}
-
 // bf16 [rows, Dp] row-major -> boxes of box_rows x 64 elements, 128-byte swizzle, zero fill out of bounds
 static int make_map(CUtensorMap* map, const __nv_bfloat16* base, int rows, int Dp, int box_rows) {
     const cuuint64_t dims[2] = {(cuuint64_t)Dp, (cuuint64_t)rows};
@@ -527,7 +496,9 @@ int das_kcenter_filter_bytes(int N, int D, int rows, size_t* bytes) {
     return DAS_OK;
 }
 
-int das_kcenter_filter_build(const float* feats, int N, int D, int row_begin, int row_end, void* filter, void* stream) {
+int das_kcenter_filter_build(das_handle* h, const float* feats, int N, int D, int row_begin, int row_end, void* filter,
+                             void* stream) {
+    DAS_ENTER(h);
     if (feats == nullptr || filter == nullptr) return DAS_ERR_INVALID_ARG;
     if (N <= 0 || D <= 0 || row_begin < 0 || row_end > N || row_begin >= row_end) return DAS_ERR_INVALID_ARG;
     if ((reinterpret_cast<uintptr_t>(filter) & 1023u) != 0) return DAS_ERR_MISALIGNED;
@@ -547,8 +518,8 @@ int das_kcenter_filter_build(const float* feats, int N, int D, int row_begin, in
     CUtensorMap tmA, tmB;
     int rc = make_map(&tmA, fb + (size_t)row_begin * L.Dp, rows, L.Dp, kBM);  // A: this rank's rows (fast output index)
     if (rc != DAS_OK) return rc;
-    const char* e2 = getenv("DAS_GEMM_2CTA");  // "0" = one CTA per 128 x 256 tile (A/B measurements, tests of both kernels)
-    if (e2 == nullptr || e2[0] != '0') {
+    // DAS_OPT_GEMM_2CTA = 0: one CTA per 128 x 256 tile (A/B measurements, tests of both kernels)
+    if (h->opt[DAS_OPT_GEMM_2CTA]) {
         rc = make_map(&tmB, fb, N, L.Dp, 128);  // B: every row (the candidate centres), 128-row halves
         if (rc != DAS_OK) return rc;
         CUtensorMap tmOut;  // dt [N centres, ld] fp32, valid width = rows; boxes of 32 centres x 128 rows
@@ -561,7 +532,7 @@ int das_kcenter_filter_build(const float* feats, int N, int D, int row_begin, in
         }
         DAS_CUDA(cudaFuncSetAttribute(kc_dist_gemm2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGemm2Smem));
         const int tiles = ((rows + 255) / 256) * ((N + 255) / 256);
-        const int pairs = tiles < kNumSMs / 2 ? tiles : kNumSMs / 2;
+        const int pairs = tiles < h->num_sms / 2 ? tiles : h->num_sms / 2;
         DAS_LAUNCH(kc_dist_gemm2_kernel, 2 * pairs, kGemmThreads, kGemm2Smem, st, tmA, tmB, tmOut, nrm32 + row_begin, nrm32, dt,
                    rows, N, L.ld, L.Dp / kBK);
         DAS_CHECK_LAUNCH();
@@ -571,7 +542,7 @@ int das_kcenter_filter_build(const float* feats, int N, int D, int row_begin, in
     if (rc != DAS_OK) return rc;
     DAS_CUDA(cudaFuncSetAttribute(kc_dist_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGemmSmem));
     const int tiles = ((rows + kBM - 1) / kBM) * ((N + kBN - 1) / kBN);
-    const int grid = tiles < kNumSMs ? tiles : kNumSMs;
+    const int grid = tiles < h->num_sms ? tiles : h->num_sms;
     DAS_LAUNCH(kc_dist_gemm_kernel, grid, kGemmThreads, kGemmSmem, st, tmA, tmB, nrm32 + row_begin, nrm32, dt, rows, N,
                L.ld, L.Dp / kBK);
     DAS_CHECK_LAUNCH();

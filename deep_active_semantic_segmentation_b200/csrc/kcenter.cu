@@ -492,15 +492,15 @@ __global__ void kcenter_sqrt_kernel(const double* d2, int n, double* d) {
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) d[i] = sqrt(d2[i]);
 }
 
-static int kc_grid(int rows) {
+static int kc_grid(const das_handle* h, int rows) {
     const int want = (rows + kKcWarps - 1) / kKcWarps;
-    const int cap = kNumSMs * 4;
+    const int cap = h->num_sms * 4;
     return want < cap ? (want < 1 ? 1 : want) : cap;
 }
 // filtered step: one thread per row
-static int kc_fgrid(int rows) {
+static int kc_fgrid(const das_handle* h, int rows) {
     const int want = (rows + kKcThreads - 1) / kKcThreads;
-    const int cap = kNumSMs * 4;
+    const int cap = h->num_sms * 4;
     return want < cap ? (want < 1 ? 1 : want) : cap;
 }
 static bool kc_vec4(const float* feats, int D) { return D % 4 == 0 && aligned16(feats); }
@@ -509,10 +509,10 @@ struct KcWorkspace {
     KcBest* best[2];
     double* d2;
 };
-static KcWorkspace kc_carve(void* ws, int N) {
+static KcWorkspace kc_carve(const das_handle* h, void* ws, int N) {
     KcWorkspace w;
     char* p = static_cast<char*>(ws);
-    const size_t tbl = align_up((size_t)kNumSMs * 4 * sizeof(KcBest), 256);
+    const size_t tbl = align_up((size_t)h->num_sms * 4 * sizeof(KcBest), 256);
     w.best[0] = reinterpret_cast<KcBest*>(p);
     w.best[1] = reinterpret_cast<KcBest*>(p + tbl);
     w.d2 = reinterpret_cast<double*>(p + 2 * tbl);
@@ -575,35 +575,25 @@ static int kc_launch_fstep(bool v4, int grid, cudaStream_t st, const float* feat
 
 using namespace das;
 
-// DAS_KC_CLUSTER=0 forces the chain-of-launches greedy loop (A/B measurements, tests of both paths)
-static bool kc_cluster_enabled() {
-    const char* e = getenv("DAS_KC_CLUSTER");
-    return e == nullptr || e[0] != '0';
-}
-
-// scratch table for the step-wise (multi-GPU) entry points: one per process is enough because the
-// ABI is thread-compatible, not thread-safe.
-static KcBest* g_step_tables[64] = {nullptr};  // one per device ordinal
-static KcBest* g_step_table = nullptr;         // the current device's table (set by ensure_step_table)
-static int ensure_step_table() {
-    int dev = 0;
-    DAS_CUDA(cudaGetDevice(&dev));
-    if (dev < 0 || dev >= 64) return DAS_ERR_UNSUPPORTED;
-    if (g_step_tables[dev] == nullptr) DAS_CUDA(cudaMalloc(&g_step_tables[dev], (size_t)kNumSMs * 4 * sizeof(KcBest)));
-    g_step_table = g_step_tables[dev];
+// scratch table of the step-wise (multi-GPU) entry points: owned by the handle, allocated on first use
+static int ensure_step_table(das_handle* h, KcBest** table) {
+    if (h->kc_step_table == nullptr) DAS_CUDA(cudaMalloc(&h->kc_step_table, (size_t)h->num_sms * 4 * sizeof(KcBest)));
+    *table = static_cast<KcBest*>(h->kc_step_table);
     return DAS_OK;
 }
 
 extern "C" {
 
-int das_kcenter_init(const float* feats, int N, int D, int row_begin, int row_end, const int32_t* centers, int L,
-                     double* min_d2, unsigned long long* key2, const void* filter, void* stream) {
+int das_kcenter_init(das_handle* h, const float* feats, int N, int D, int row_begin, int row_end, const int32_t* centers,
+                     int L, double* min_d2, unsigned long long* key2, const void* filter, void* stream) {
+    DAS_ENTER(h);
     if (feats == nullptr || centers == nullptr || min_d2 == nullptr || key2 == nullptr) return DAS_ERR_INVALID_ARG;
     if (N <= 0 || D <= 0 || L <= 0 || row_begin < 0 || row_end > N || row_begin >= row_end) return DAS_ERR_INVALID_ARG;
-    int rc = ensure_step_table();
+    KcBest* g_step_table = nullptr;
+    int rc = ensure_step_table(h, &g_step_table);
     if (rc != DAS_OK) return rc;
     cudaStream_t st = (cudaStream_t)stream;
-    const int grid = kc_grid(row_end - row_begin);
+    const int grid = kc_grid(h, row_end - row_begin);
     if (filter != nullptr)
         rc = kc_launch_finit(kc_vec4(feats, D), grid, st, feats, D, row_begin, row_end, centers, L, min_d2, g_step_table,
                              kc_filter_view(filter, N, D, row_end - row_begin));
@@ -616,20 +606,23 @@ int das_kcenter_init(const float* feats, int N, int D, int row_begin, int row_en
     return DAS_OK;
 }
 
-int das_kcenter_step(const float* feats, int N, int D, int row_begin, int row_end, const int32_t* centre_idx,
-                     double* min_d2, unsigned long long* key2, const void* filter, void* stream) {
+int das_kcenter_step(das_handle* h, const float* feats, int N, int D, int row_begin, int row_end,
+                     const int32_t* centre_idx, double* min_d2, unsigned long long* key2, const void* filter,
+                     void* stream) {
+    DAS_ENTER(h);
     if (feats == nullptr || centre_idx == nullptr || min_d2 == nullptr || key2 == nullptr) return DAS_ERR_INVALID_ARG;
     if (N <= 0 || D <= 0 || row_begin < 0 || row_end > N || row_begin >= row_end) return DAS_ERR_INVALID_ARG;
-    int rc = ensure_step_table();
+    KcBest* g_step_table = nullptr;
+    int rc = ensure_step_table(h, &g_step_table);
     if (rc != DAS_OK) return rc;
     cudaStream_t st = (cudaStream_t)stream;
     int grid;
     if (filter != nullptr) {
-        grid = kc_fgrid(row_end - row_begin);
+        grid = kc_fgrid(h, row_end - row_begin);
         rc = kc_launch_fstep<1>(kc_vec4(feats, D), grid, st, feats, D, row_begin, row_end, centre_idx, min_d2, nullptr, 0,
                                 g_step_table, nullptr, 0, kc_filter_view(filter, N, D, row_end - row_begin));
     } else {
-        grid = kc_grid(row_end - row_begin);
+        grid = kc_grid(h, row_end - row_begin);
         rc = kc_launch<1>(kc_vec4(feats, D), grid, st, feats, D, row_begin, row_end, centre_idx, 1, min_d2, nullptr, 0,
                           g_step_table, nullptr, 0);
     }
@@ -639,27 +632,29 @@ int das_kcenter_step(const float* feats, int N, int D, int row_begin, int row_en
     return DAS_OK;
 }
 
-int das_kcenter_workspace_bytes(int N, int D, size_t* bytes) {
+int das_kcenter_workspace_bytes(const das_handle* h, int N, int D, size_t* bytes) {
+    if (h == nullptr || h->magic != kDasHandleMagic) return DAS_ERR_INVALID_ARG;
     if (bytes == nullptr || N <= 0 || D <= 0) return DAS_ERR_INVALID_ARG;
-    *bytes = 2 * align_up((size_t)kNumSMs * 4 * sizeof(KcBest), 256) + align_up((size_t)N * sizeof(double), 256);
+    *bytes = 2 * align_up((size_t)h->num_sms * 4 * sizeof(KcBest), 256) + align_up((size_t)N * sizeof(double), 256);
     return DAS_OK;
 }
 
-int das_kcenter_greedy(const float* feats, int N, int D, const int32_t* centers, int L, int K, int32_t* picks,
-                       double* min_d, void* workspace, const void* filter, void* stream) {
+int das_kcenter_greedy(das_handle* h, const float* feats, int N, int D, const int32_t* centers, int L, int K,
+                       int32_t* picks, double* min_d, void* workspace, const void* filter, void* stream) {
+    DAS_ENTER(h);
     if (feats == nullptr || centers == nullptr || picks == nullptr || min_d == nullptr || workspace == nullptr)
         return DAS_ERR_INVALID_ARG;
     if (N <= 0 || D <= 0 || L <= 0 || K < 0) return DAS_ERR_INVALID_ARG;
     cudaStream_t st = (cudaStream_t)stream;
-    const KcWorkspace w = kc_carve(workspace, N);
+    const KcWorkspace w = kc_carve(h, workspace, N);
     const bool v4 = kc_vec4(feats, D);
     int rc;
     if (filter != nullptr) {
         const KcFilter f = kc_filter_view(filter, N, D, N);
-        int grid = kc_grid(N);
+        int grid = kc_grid(h, N);
         rc = kc_launch_finit(v4, grid, st, feats, D, 0, N, centers, L, w.d2, w.best[0], f);
         if (rc != DAS_OK) return rc;
-        if (N <= kClCtas * kClThreads * kClRows && kc_cluster_enabled()) {
+        if (N <= kClCtas * kClThreads * kClRows && h->opt[DAS_OPT_KC_CLUSTER]) {
             // the whole loop inside one thread-block cluster
             const size_t row_bytes = (size_t)D * sizeof(float);
             const int stage_centre = row_bytes <= 96 * 1024 ? 1 : 0;
@@ -677,7 +672,7 @@ int das_kcenter_greedy(const float* feats, int N, int D, const int32_t* centers,
             return DAS_OK;
         }
         int n_prev = grid;
-        grid = kc_fgrid(N);
+        grid = kc_fgrid(h, N);
         for (int s = 0; s < K; ++s) {
             rc = kc_launch_fstep<2>(v4, grid, st, feats, D, 0, N, nullptr, w.d2, w.best[s & 1], n_prev, w.best[(s + 1) & 1],
                                     picks, s, f);
@@ -685,7 +680,7 @@ int das_kcenter_greedy(const float* feats, int N, int D, const int32_t* centers,
             n_prev = grid;
         }
     } else {
-        const int grid = kc_grid(N);
+        const int grid = kc_grid(h, N);
         rc = kc_launch<0>(v4, grid, st, feats, D, 0, N, centers, L, w.d2, nullptr, 0, w.best[0], nullptr, 0);
         if (rc != DAS_OK) return rc;
         for (int s = 0; s < K; ++s) {
@@ -694,13 +689,15 @@ int das_kcenter_greedy(const float* feats, int N, int D, const int32_t* centers,
             if (rc != DAS_OK) return rc;
         }
     }
-    DAS_LAUNCH(kcenter_sqrt_kernel, kc_grid(N), kKcThreads, 0, st, w.d2, N, min_d);
+    DAS_LAUNCH(kcenter_sqrt_kernel, kc_grid(h, N), kKcThreads, 0, st, w.d2, N, min_d);
     DAS_CHECK_LAUNCH();
     return DAS_OK;
 }
 
 /* host copy of the filter counters: stats[0] = rows re-evaluated exactly, stats[1] = rows screened */
-int das_kcenter_filter_stats(const void* filter, int N, int D, int rows, unsigned long long* stats2, void* stream) {
+int das_kcenter_filter_stats(das_handle* h, const void* filter, int N, int D, int rows, unsigned long long* stats2,
+                             void* stream) {
+    DAS_ENTER(h);
     if (filter == nullptr || stats2 == nullptr || N <= 0 || D <= 0 || rows <= 0 || rows > N) return DAS_ERR_INVALID_ARG;
     const KcFilter f = kc_filter_view(filter, N, D, rows);
     DAS_CUDA(cudaMemcpyAsync(stats2, f.stats, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, (cudaStream_t)stream));

@@ -57,8 +57,10 @@ __global__ void __launch_bounds__(kMsThreads) ms_score_kernel(const T* __restric
                                                               double* __restrict__ scores) {
     __shared__ double red[kMsThreads / 32];
     const int i = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const T* prev = step > 0 ? dist + (size_t)picks[step - 1] * N : nullptr;
-    const bool skip = selected[i] != 0 || (step > 0 && picks[step - 1] == i);
+    // picks[step - 1] == -1: every candidate was already taken (k > M), there is no previous pick to fold in
+    const int last = step > 0 ? picks[step - 1] : -1;
+    const T* prev = last >= 0 ? dist + (size_t)last * N : nullptr;
+    const bool skip = selected[i] != 0 || last == i;
     const T* mine = dist + (size_t)i * N;
     double s = 0.0;
     for (int n = tid; n < N; n += kMsThreads) {
@@ -84,7 +86,7 @@ __global__ void __launch_bounds__(1024) ms_pick_kernel(const double* __restrict_
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     double bv = INFINITY;
     int bi = 0x7fffffff;
-    if (step > 0 && tid == 0) selected[picks[step - 1]] = 1;
+    if (step > 0 && tid == 0 && picks[step - 1] >= 0) selected[picks[step - 1]] = 1;
     for (int i = tid; i < M; i += 1024) {
         const double v = scores[i];
         if (v < bv || (v == bv && i < bi)) bv = v, bi = i;
@@ -157,8 +159,9 @@ int das_maxsubset_workspace_bytes(int N, int M, int D, int is_f64, size_t* bytes
     return DAS_OK;
 }
 
-int das_maxsubset_greedy(const void* X, const void* Y, int N, int M, int D, int is_f64, int k, int32_t* picks, void* workspace,
-                         void* stream) {
+int das_maxsubset_greedy(das_handle* h, const void* X, const void* Y, int N, int M, int D, int is_f64, int k, int32_t* picks,
+                         void* workspace, void* stream) {
+    DAS_ENTER(h);
     if (X == nullptr || Y == nullptr || picks == nullptr || workspace == nullptr) return DAS_ERR_INVALID_ARG;
     if (N <= 0 || M <= 0 || D <= 0 || k < 0) return DAS_ERR_INVALID_ARG;
     if (M > 65535 * 32) return DAS_ERR_UNSUPPORTED;

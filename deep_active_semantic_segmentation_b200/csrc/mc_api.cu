@@ -8,9 +8,6 @@
 
 namespace das {
 
-int g_last_cuda_error = 0;
-unsigned long long g_launch_count = 0;
-
 // class-count ranges compiled in separate translation units (see build.py)
 #define DAS_DECL_RANGE(LO, HI)                                                                         \
     int dispatch_accumulate_##LO##_##HI(const McAccParams&, int, int, int, cudaStream_t);             \
@@ -221,20 +218,9 @@ static int reduce_partials(const das_mc_desc* desc, const McFinParams& p, float*
 }
 
 // ---- TMA-staged single-shot path -------------------------------------------------------------
-static McTmaParams g_tma_params;  // 4.3 KB: kept off the stack; the ABI is thread-compatible, not thread-safe
-
-// DAS_MC_TMA=0 forces the LDG kernel (A/B measurements, tests of both paths); DAS_MC_TMA_CTAS = CTAs per SM
-static bool tma_enabled() {
-    const char* e = getenv("DAS_MC_TMA");
-    return e == nullptr || e[0] != '0';
-}
-static int tma_ctas_per_sm() {
-    const char* e = getenv("DAS_MC_TMA_CTAS");
-    const int v = e != nullptr ? atoi(e) : 0;  // 0 = per class count (mc_tma.cuh)
-    return v >= 1 && v <= 8 ? v : 0;
-}
-static bool tma_eligible(const das_mc_desc* desc, const McScoreParams& q) {
-    if (!tma_enabled() || q.acc.pass_begin != 0) return false;
+// DAS_OPT_MC_TMA = 0 forces the LDG kernel (A/B measurements, tests of both paths); DAS_OPT_MC_TMA_CTAS = CTAs per SM
+static bool tma_eligible(const das_handle* h, const das_mc_desc* desc, const McScoreParams& q) {
+    if (!h->opt[DAS_OPT_MC_TMA] || q.acc.pass_begin != 0) return false;
     // vote-only scoring has no softmax work to overlap: its LDG kernel already runs at the copy roofline
     // (measured 1.00 vs 0.98 for the ring on 513 x 513 planes)
     if (!(desc->flags & DAS_MC_PROBS)) return false;
@@ -246,25 +232,27 @@ static bool tma_eligible(const das_mc_desc* desc, const McScoreParams& q) {
         if (!aligned16(q.acc.logits[g])) return false;
     return true;
 }
-static int fill_tma_params(const das_mc_desc* desc, const McScoreParams& q, McTmaParams* out) {
+static int fill_tma_params(das_handle* h, const das_mc_desc* desc, const McScoreParams& q, McTmaParams* out) {
     const unsigned long long HW = (unsigned long long)desc->H * desc->W;
     const bool flat = HW % 4 != 0;  // plane strides are not multiples of 16 bytes: address by element instead
     for (int g = 0; g < q.acc.n_passes; ++g) {
-        int rc;
+        int rc = DAS_OK;
+        const CUtensorMap* m;   // descriptors are cached per (buffer, shape) in the handle
         if (!flat) {
             const cuuint64_t dims[3] = {HW, (cuuint64_t)desc->C, (cuuint64_t)desc->B};
             const cuuint64_t strides[2] = {HW * sizeof(float), HW * desc->C * sizeof(float)};
             const cuuint32_t box[3] = {(cuuint32_t)kTmaPix, (cuuint32_t)desc->C, 1};
-            rc = make_tensor_map(&out->maps[g], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, q.acc.logits[g], dims, strides, box,
-                                 CU_TENSOR_MAP_SWIZZLE_NONE);
+            m = cached_tensor_map(h, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, q.acc.logits[g], dims, strides, box,
+                                  CU_TENSOR_MAP_SWIZZLE_NONE, &rc);
         } else {
             const cuuint64_t dims[1] = {HW * desc->C * desc->B};
             const cuuint64_t strides[1] = {0};
             const cuuint32_t box[1] = {(cuuint32_t)kTmaPix};
-            rc = make_tensor_map(&out->maps[g], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 1, q.acc.logits[g], dims, strides, box,
-                                 CU_TENSOR_MAP_SWIZZLE_NONE);
+            m = cached_tensor_map(h, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 1, q.acc.logits[g], dims, strides, box,
+                                  CU_TENSOR_MAP_SWIZZLE_NONE, &rc);
         }
-        if (rc != DAS_OK) return rc;
+        if (m == nullptr) return rc != DAS_OK ? rc : DAS_ERR_CUDA;
+        out->maps[g] = *m;
     }
     out->fin = q.fin;
     out->HW = (long long)HW;
@@ -273,11 +261,11 @@ static int fill_tma_params(const das_mc_desc* desc, const McScoreParams& q, McTm
     out->tiles_per_image = q.fin.blocks_per_image;  // 256-pixel tiles (the VEC=2 LDG kernel's partition) or 252 (flat)
     out->stages = 0;
     out->flat = flat ? 1 : 0;
+    out->num_sms = h->num_sms;
     return DAS_OK;
 }
 
 // ---- fused bilinear upsample (low-resolution logits) --------------------------------------------
-static McUpParams g_up_params;
 
 // ATen's align_corners scale (area_pixel_compute_scale<float>)
 static float up_scale(int n_in, int n_out) { return n_out > 1 ? (float)(n_in - 1) / (float)(n_out - 1) : 0.f; }
@@ -308,31 +296,16 @@ static bool up_supported(int h, int w, int H, int W, int nw) {
 }
 // consumer warps per CTA (0 = the shape is not supported).  15 (one 512-thread CTA per SM, tile 16 x 60, one
 // producer warp per SM) measured 3-8 % faster than 4 (three 160-thread CTAs per SM, tile 16 x 16) on 512 x 1024 and
-// 513 x 513 outputs (profiles/r1_upsample_notes.md); narrow outputs keep the small tile.  DAS_MC_UP_WARPS = 4 | 15
+// 513 x 513 outputs (profiles/r1_upsample_notes.md); narrow outputs keep the small tile.  DAS_OPT_MC_UP_WARPS = 4 | 15
 // overrides the choice.
-static int up_warps(int h, int w, int H, int W) {
-    const char* e = getenv("DAS_MC_UP_WARPS");
-    const int v = e != nullptr ? atoi(e) : 0;
+static int up_warps(const das_handle* hd, int h, int w, int H, int W) {
+    const int v = hd != nullptr ? hd->opt[DAS_OPT_MC_UP_WARPS] : 0;
     if (v == 4 || v == 15) return up_supported(h, w, H, W, v) ? v : 0;
     if (W >= 2 * up_tile_w(15) && up_supported(h, w, H, W, 15)) return 15;
     return up_supported(h, w, H, W, 4) ? 4 : 0;
 }
 
 extern "C" {
-
-const char* das_strerror(int status) {
-    switch (status) {
-        case DAS_OK: return "ok";
-        case DAS_ERR_INVALID_ARG: return "invalid argument";
-        case DAS_ERR_UNSUPPORTED: return "unsupported size (see DAS_MAX_* in das_b200.h)";
-        case DAS_ERR_CUDA: return "CUDA runtime error (see das_last_cuda_error)";
-        case DAS_ERR_MISALIGNED: return "pointer not aligned as documented";
-        default: return "unknown das_status";
-    }
-}
-int das_abi_version(void) { return DAS_ABI_VERSION; }
-int das_last_cuda_error(void) { return g_last_cuda_error; }
-uint64_t das_launch_count(void) { return g_launch_count; }
 
 int das_mc_state_bytes(const das_mc_desc* desc, size_t* bytes) {
     int rc = mc_validate(desc);
@@ -342,7 +315,8 @@ int das_mc_state_bytes(const das_mc_desc* desc, size_t* bytes) {
     return DAS_OK;
 }
 
-int das_mc_reset(const das_mc_desc* desc, void* state, void* stream) {
+int das_mc_reset(das_handle* h, const das_mc_desc* desc, void* state, void* stream) {
+    DAS_ENTER(h);
     int rc = mc_validate(desc);
     if (rc != DAS_OK) return rc;
     if (state == nullptr) return DAS_ERR_INVALID_ARG;
@@ -350,8 +324,9 @@ int das_mc_reset(const das_mc_desc* desc, void* state, void* stream) {
     return DAS_OK;
 }
 
-int das_mc_accumulate(const das_mc_desc* desc, void* state, const float* const* pass_logits, int n_passes,
-                      int pass_begin, void* stream) {
+int das_mc_accumulate(das_handle* h, const das_mc_desc* desc, void* state, const float* const* pass_logits,
+                      int n_passes, int pass_begin, void* stream) {
+    DAS_ENTER(h);
     int rc = mc_validate(desc);
     if (rc != DAS_OK) return rc;
     if (desc->flags & DAS_MC_SINGLE_SHOT) return DAS_ERR_INVALID_ARG;
@@ -362,9 +337,10 @@ int das_mc_accumulate(const das_mc_desc* desc, void* state, const float* const* 
                                (cudaStream_t)stream);
 }
 
-int das_mc_finalize(const das_mc_desc* desc, void* state, const float* labels, int T, float* vote_entropy,
-                    float* pred_entropy, float* bald, float* confidence, float* margin, uint8_t* weak_labels,
-                    float* image_scores, void* stream) {
+int das_mc_finalize(das_handle* h, const das_mc_desc* desc, void* state, const float* labels, int T,
+                    float* vote_entropy, float* pred_entropy, float* bald, float* confidence, float* margin,
+                    uint8_t* weak_labels, float* image_scores, void* stream) {
+    DAS_ENTER(h);
     int rc = mc_validate(desc);
     if (rc != DAS_OK) return rc;
     if (desc->flags & DAS_MC_SINGLE_SHOT) return DAS_ERR_INVALID_ARG;
@@ -378,10 +354,11 @@ int das_mc_finalize(const das_mc_desc* desc, void* state, const float* labels, i
     return reduce_partials(desc, p, image_scores, st);
 }
 
-int das_mc_accumulate_finalize(const das_mc_desc* desc, void* state, const float* const* pass_logits, int n_passes,
-                               int pass_begin, const float* labels, float* vote_entropy, float* pred_entropy,
-                               float* bald, float* confidence, float* margin, uint8_t* weak_labels,
-                               float* image_scores, void* stream) {
+int das_mc_accumulate_finalize(das_handle* h, const das_mc_desc* desc, void* state, const float* const* pass_logits,
+                               int n_passes, int pass_begin, const float* labels, float* vote_entropy,
+                               float* pred_entropy, float* bald, float* confidence, float* margin,
+                               uint8_t* weak_labels, float* image_scores, void* stream) {
+    DAS_ENTER(h);
     int rc = mc_validate(desc);
     if (rc != DAS_OK) return rc;
     if ((desc->flags & DAS_MC_SINGLE_SHOT) && pass_begin != 0) return DAS_ERR_INVALID_ARG;
@@ -393,16 +370,17 @@ int das_mc_accumulate_finalize(const das_mc_desc* desc, void* state, const float
     if (rc != DAS_OK) return rc;
     cudaStream_t st = (cudaStream_t)stream;
     const int flags = desc->flags & (DAS_MC_VOTES | DAS_MC_PROBS);
-    if (tma_eligible(desc, q)) {
+    if (tma_eligible(h, desc, q)) {
         // whole Monte-Carlo stack in one launch and 16-byte aligned planes: TMA-staged persistent kernel
         {
             const long long HW = (long long)desc->H * desc->W;
             const int tile = HW % 4 == 0 ? kTmaPix : kTmaFlatPix;
             q.fin.blocks_per_image = (int)((HW + tile - 1) / tile);
         }
-        rc = fill_tma_params(desc, q, &g_tma_params);
+        McTmaParams tp;
+        rc = fill_tma_params(h, desc, q, &tp);
         if (rc != DAS_OK) return rc;
-        rc = dispatch_score_tma(g_tma_params, flags, tma_ctas_per_sm(), st);
+        rc = dispatch_score_tma(tp, flags, h->opt[DAS_OPT_MC_TMA_CTAS], st);
     } else {
         rc = dispatch_score(q, desc->B, acc_vec(*desc), flags, st);
     }
@@ -410,24 +388,27 @@ int das_mc_accumulate_finalize(const das_mc_desc* desc, void* state, const float
     return reduce_partials(desc, q.fin, image_scores, st);
 }
 
-int das_mc_upsample_supported(int h, int w, int H, int W) {
-    return up_warps(h, w, H, W) != 0 ? 1 : 0;
+int das_mc_upsample_supported(const das_handle* hd, int h, int w, int H, int W) {
+    if (hd != nullptr && hd->magic != kDasHandleMagic) return 0;
+    return up_warps(hd, h, w, H, W) != 0 ? 1 : 0;  // hd == NULL: the default options (host-only question)
 }
 
-int das_mc_upsample_accumulate_finalize(const das_mc_desc* desc, void* state, const float* const* pass_lowres_logits,
-                                        int n_passes, int h, int w, const float* labels, float* vote_entropy,
-                                        float* pred_entropy, float* bald, float* confidence, float* margin,
-                                        uint8_t* weak_labels, float* image_scores, void* stream) {
+int das_mc_upsample_accumulate_finalize(das_handle* hd, const das_mc_desc* desc, void* state,
+                                        const float* const* pass_lowres_logits, int n_passes, int h, int w,
+                                        const float* labels, float* vote_entropy, float* pred_entropy, float* bald,
+                                        float* confidence, float* margin, uint8_t* weak_labels, float* image_scores,
+                                        void* stream) {
+    DAS_ENTER(hd);
     int rc = mc_validate(desc);
     if (rc != DAS_OK) return rc;
     if (pass_lowres_logits == nullptr || h < 1 || w < 1) return DAS_ERR_INVALID_ARG;
     if (n_passes < 1 || n_passes > desc->T_cap) return DAS_ERR_INVALID_ARG;
     if (n_passes > DAS_MAX_PASS_GROUP) return DAS_ERR_UNSUPPORTED;
-    const int nw = up_warps(h, w, desc->H, desc->W);
+    const int nw = up_warps(hd, h, w, desc->H, desc->W);
     if (nw == 0) return DAS_ERR_UNSUPPORTED;
     // source offsets inside one image are formed in 32 bits
     if ((unsigned long long)desc->C * h * w >= (1ull << 31)) return DAS_ERR_UNSUPPORTED;
-    McUpParams& q = g_up_params;
+    McUpParams q;
     const int tiles_x = (desc->W + up_tile_w(nw) - 1) / up_tile_w(nw), tiles_y = (desc->H + kUpTileH - 1) / kUpTileH;
     rc = fill_fin_params(desc, state, labels, n_passes, vote_entropy, pred_entropy, bald, confidence, margin,
                          weak_labels, tiles_x * tiles_y, &q.fin);
@@ -443,6 +424,7 @@ int das_mc_upsample_accumulate_finalize(const das_mc_desc* desc, void* state, co
     q.h = h, q.w = w, q.H = desc->H, q.W = desc->W;
     q.tiles_x = tiles_x, q.tiles_y = tiles_y;
     q.rh = up_scale(h, desc->H), q.rw = up_scale(w, desc->W);
+    q.num_sms = hd->num_sms;
     cudaStream_t st = (cudaStream_t)stream;
     rc = dispatch_score_up(q, desc->flags & (DAS_MC_VOTES | DAS_MC_PROBS), nw, st);
     if (rc != DAS_OK) return rc;

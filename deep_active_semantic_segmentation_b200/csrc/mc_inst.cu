@@ -146,7 +146,7 @@ int launch_score_tma(const McTmaParams& p, int flags, int ctas_per_sm, cudaStrea
         if (e__ != cudaSuccess) return cuda_fail(e__);                                             \
         if (occ__ < 1) return DAS_ERR_UNSUPPORTED;                                                 \
         if (occ__ > ctas_per_sm) occ__ = ctas_per_sm;                                              \
-        const int grid__ = tiles < kNumSMs * occ__ ? tiles : kNumSMs * occ__;                      \
+        const int grid__ = tiles < q.num_sms * occ__ ? tiles : q.num_sms * occ__;                      \
         DAS_LAUNCH((mc_score_tma_kernel<C, P, Q, A>), grid__, kTmaThreads, smem, st, q);           \
     } while (0)
     if (!p.flat) {
@@ -184,7 +184,7 @@ int launch_score_up_nw(const McUpParams& p, int flags, cudaStream_t st) {
         if (e__ != cudaSuccess) return cuda_fail(e__);                                             \
         if (occ__ < 1) return DAS_ERR_UNSUPPORTED;                                                 \
         if (occ__ > MINB) occ__ = MINB;                                                            \
-        const int grid__ = tiles < kNumSMs * occ__ ? tiles : kNumSMs * occ__;                      \
+        const int grid__ = tiles < q.num_sms * occ__ ? tiles : q.num_sms * occ__;                      \
         DAS_LAUNCH((mc_score_up_kernel<C, P, Q, NW, MINB>), grid__, up_threads(NW), smem, st, q);  \
     } while (0)
     if (probs && votes) DAS_UP(true, true);

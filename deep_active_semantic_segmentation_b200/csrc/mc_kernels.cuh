@@ -189,14 +189,16 @@ __device__ __forceinline__ uint32_t mc_pass_math(float (&x)[C][VEC], Acc<C, VEC,
         }
         m[j] = t[0];
     }
-    // d_c = x_c - m: exactly +0 for the maxima, negative otherwise (IEEE subtraction of distinct floats is never 0),
-    // so the sign bits ARE the "not a maximum" flags: one funnel shift per class collects them (instead of a
+    // d_c = x_c + (0 - m): exactly +0 for the maxima, negative otherwise (IEEE subtraction of distinct floats is never
+    // 0), so the sign bits ARE the "not a maximum" flags: one funnel shift per class collects them (instead of a
     // compare + select), the first maximum is the highest clear bit.  The softmax reuses d: y = d * log2(e).
+    // `0 - m` (not `-m`): for m = +-0 it is +0, so a logit of -0 next to a maximum of +0 gives (-0) + (+0) = +0 - torch's
+    // argmax compares -0 == +0 and takes the first of them (mc_dropout.py:40); `-m` would give (-0) + (-0) = -0.
     if constexpr (VEC % 2 == 0) {
 #pragma unroll
         for (int h = 0; h < VEC / 2; ++h) {
             const int j0 = 2 * h, j1 = 2 * h + 1;
-            const f32x2 nm = {-m[j0], -m[j1]};
+            const f32x2 nm = {0.f - m[j0], 0.f - m[j1]};
 #pragma unroll
             for (int c = 0; c < C; ++c) {
                 const f32x2 d = add2(f32x2{x[c][j0], x[c][j1]}, nm);
@@ -205,9 +207,11 @@ __device__ __forceinline__ uint32_t mc_pass_math(float (&x)[C][VEC], Acc<C, VEC,
         }
     } else {
 #pragma unroll
-        for (int j = 0; j < VEC; ++j)
+        for (int j = 0; j < VEC; ++j) {
+            const float nm = 0.f - m[j];
 #pragma unroll
-            for (int c = 0; c < C; ++c) x[c][j] = x[c][j] - m[j];
+            for (int c = 0; c < C; ++c) x[c][j] = x[c][j] + nm;
+        }
     }
     if (VOTES) {
 #pragma unroll

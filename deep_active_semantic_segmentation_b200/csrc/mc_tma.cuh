@@ -33,6 +33,7 @@ struct McTmaParams {
     McFinParams fin;
     long long HW;
     int B, n_passes, tiles_per_image, stages, flat;
+    int num_sms;  // host only: persistent grid = min(tiles, num_sms * CTAs per SM)
 };
 
 __device__ __forceinline__ uint32_t tma_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }

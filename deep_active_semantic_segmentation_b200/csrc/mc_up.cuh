@@ -50,6 +50,7 @@ struct McUpParams {
     int B, n_passes, stages;
     int h, w, H, W, tiles_x, tiles_y;
     float rh, rw;                             // float(h-1)/float(H-1), float(w-1)/float(W-1)  (0 when H / W == 1)
+    int num_sms;                              // host only: persistent grid sizing
 };
 
 // ATen: source index and the weights of the two neighbours for destination index d (align_corners=True)

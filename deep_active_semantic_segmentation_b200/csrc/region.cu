@@ -209,7 +209,8 @@ using namespace das;
 
 extern "C" {
 
-int das_suppress_rects(float* maps, int B, int H, int W, const int32_t* rects, int n, void* stream) {
+int das_suppress_rects(das_handle* h, float* maps, int B, int H, int W, const int32_t* rects, int n, void* stream) {
+    DAS_ENTER(h);
     if (maps == nullptr || B <= 0 || H <= 0 || W <= 0 || n < 0 || (n > 0 && rects == nullptr)) return DAS_ERR_INVALID_ARG;
     if (n == 0) return DAS_OK;
     DAS_LAUNCH(suppress_rects_kernel, n, 256, 0, (cudaStream_t)stream, maps, B, H, W, rects, n);
@@ -217,10 +218,11 @@ int das_suppress_rects(float* maps, int B, int H, int W, const int32_t* rects, i
     return DAS_OK;
 }
 
-int das_add_maps(float* a, const float* b, size_t n, void* stream) {
+int das_add_maps(das_handle* h, float* a, const float* b, size_t n, void* stream) {
+    DAS_ENTER(h);
     if (a == nullptr || b == nullptr) return DAS_ERR_INVALID_ARG;
     if (n == 0) return DAS_OK;
-    const int grid = (int)((n + 255) / 256 < (size_t)(kNumSMs * 8) ? (n + 255) / 256 : (size_t)(kNumSMs * 8));
+    const int grid = (int)((n + 255) / 256 < (size_t)(h->num_sms * 8) ? (n + 255) / 256 : (size_t)(h->num_sms * 8));
     DAS_LAUNCH(add_maps_kernel, grid, 256, 0, (cudaStream_t)stream, a, b, n);
     DAS_CHECK_LAUNCH();
     return DAS_OK;
@@ -232,15 +234,17 @@ int das_box_sum_workspace_bytes(int B, int H, int W, int R, size_t* bytes) {
     return DAS_OK;
 }
 
-int das_minmax_init(float* minmax, void* stream) {
+int das_minmax_init(das_handle* h, float* minmax, void* stream) {
+    DAS_ENTER(h);
     if (minmax == nullptr) return DAS_ERR_INVALID_ARG;
     DAS_LAUNCH(minmax_init_kernel, 1, 1, 0, (cudaStream_t)stream, minmax);
     DAS_CHECK_LAUNCH();
     return DAS_OK;
 }
 
-int das_box_sum(const float* maps, int B, int H, int W, int R, float* out, float* minmax, void* workspace,
+int das_box_sum(das_handle* h, const float* maps, int B, int H, int W, int R, float* out, float* minmax, void* workspace,
                 void* stream) {
+    DAS_ENTER(h);
     if (maps == nullptr || out == nullptr || minmax == nullptr || workspace == nullptr) return DAS_ERR_INVALID_ARG;
     if (B <= 0 || H <= 0 || W <= 0 || R <= 0 || R > H || R > W) return DAS_ERR_INVALID_ARG;
     const int H2 = H - R + 1, W2 = W - R + 1;
@@ -259,17 +263,19 @@ int das_box_sum(const float* maps, int B, int H, int W, int R, float* out, float
     return DAS_OK;
 }
 
-int das_minmax_normalise(float* score_maps, size_t n, const float* minmax, void* stream) {
+int das_minmax_normalise(das_handle* h, float* score_maps, size_t n, const float* minmax, void* stream) {
+    DAS_ENTER(h);
     if (score_maps == nullptr || minmax == nullptr) return DAS_ERR_INVALID_ARG;
     if (n == 0) return DAS_OK;
-    const int grid = (int)((n + 255) / 256 < (size_t)(kNumSMs * 8) ? (n + 255) / 256 : (size_t)(kNumSMs * 8));
+    const int grid = (int)((n + 255) / 256 < (size_t)(h->num_sms * 8) ? (n + 255) / 256 : (size_t)(h->num_sms * 8));
     DAS_LAUNCH(minmax_normalise_kernel, grid, 256, 0, (cudaStream_t)stream, score_maps, n, minmax);
     DAS_CHECK_LAUNCH();
     return DAS_OK;
 }
 
-int das_nms_sequences(float* score_maps, int N, int H2, int W2, int R, int kmax, float stop, float* cand_score,
+int das_nms_sequences(das_handle* h, float* score_maps, int N, int H2, int W2, int R, int kmax, float stop, float* cand_score,
                       int32_t* cand_rc, int32_t* cand_count, long long image_offset, int64_t* cand_flat, void* stream) {
+    DAS_ENTER(h);
     if (score_maps == nullptr || cand_score == nullptr || cand_rc == nullptr || cand_count == nullptr)
         return DAS_ERR_INVALID_ARG;
     if (N <= 0 || H2 <= 0 || W2 <= 0 || R <= 0 || kmax <= 0) return DAS_ERR_INVALID_ARG;

@@ -66,6 +66,34 @@ def gather_candidates(scores, ids, k: int):
     return out_s, out_i
 
 
+def exchange_records(rec: torch.Tensor) -> torch.Tensor:
+    """ONE all_gather_into_tensor of every rank's [k, 2] int64 candidate-record block (ops.topk_records) -> the
+    [W * k, 2] table in rank order, on the device the block came from.  Works with NCCL (CUDA) and gloo (CPU)."""
+    W, _ = world()
+    if W == 1:
+        return rec
+    dev = _comm_device()
+    send = rec.detach().to(dev).contiguous()
+    recv = torch.empty((W * send.shape[0], 2), dtype=torch.int64, device=dev)
+    td.all_gather_into_tensor(recv, send)
+    return recv.to(rec.device)
+
+
+def select_ranked(scores: torch.Tensor, k: int, descending: bool, ids: torch.Tensor | None = None, id_offset: int = 0):
+    """First k of the pool-global stable ranking from each rank's local scores: K3 on the shard (records written
+    straight into the all-gather send buffer) -> one all-gather -> K3 merge on every rank -> ONE device-to-host copy of
+    the k winners.  Returns (float32 scores, int64 global ids) numpy arrays, identical on all ranks; fewer than k when
+    the pool is smaller.  ids: per-candidate int64 payload (region flat indices), default = position + id_offset (the
+    global image index of a contiguous shard).  Ties rank by (rank, local order) = global index ascending."""
+    from . import ops
+
+    W, _ = world()
+    rec = ops.topk_records(scores, int(k), descending, ids=ids, id_offset=id_offset)
+    if W > 1:
+        rec = ops.topk_merge(exchange_records(rec), int(k), descending)
+    return ops.records_to_host(rec)
+
+
 def merge_ranked(scores, ids, k: int, descending: bool):
     """Stable global ranking of gathered candidates: score, then global index ascending - the order
     Python's stable sorted() gives on the un-sharded pool (mc_dropout.py:195, ceal.py:69)."""
@@ -111,6 +139,30 @@ def allreduce_minmax(minmax: torch.Tensor) -> torch.Tensor:
     t = torch.stack([-minmax[0], minmax[1]]).to(dev)
     td.all_reduce(t, op=td.ReduceOp.MAX)
     return torch.stack([-t[0], t[1]]).to(minmax.device)
+
+
+def all_gather_rows(local: torch.Tensor, n_total: int) -> torch.Tensor:
+    """Row blocks of a [n_total, D] matrix that is sharded by `shard_bounds` -> the whole matrix on every rank
+    (core-set: each rank forwards its slice of the images, core_set.py:56-63, then all ranks run the same greedy loop).
+    One all_gather_into_tensor of equally sized (padded) blocks; a rank with an empty shard contributes padding only."""
+    W, rank = world()
+    if W == 1:
+        return local
+    per = -(-n_total // W) if n_total > 0 else 0
+    dev = _comm_device()
+    d = torch.tensor([local.shape[1] if local.dim() == 2 and local.shape[0] > 0 else 0], dtype=torch.int64, device=dev)
+    td.all_reduce(d, op=td.ReduceOp.MAX)
+    D = int(d.item())
+    send = torch.zeros((per, D), dtype=local.dtype, device=dev)
+    if local.shape[0] > 0:
+        send[: local.shape[0]] = local.to(dev)
+    recv = torch.empty((W * per, D), dtype=local.dtype, device=dev)
+    td.all_gather_into_tensor(recv, send)
+    parts = []
+    for r in range(W):
+        lo, hi = shard_bounds(n_total, W, r)
+        parts.append(recv[r * per: r * per + (hi - lo)])
+    return torch.cat(parts).to(local.device).contiguous()
 
 
 def gather_objects(obj):

@@ -22,8 +22,27 @@ def _ptr(t):
     return C.c_void_p(t.data_ptr()) if t is not None else None
 
 
-def _stream():
-    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+def _stream(device=None):
+    """torch's current stream ON THE TENSORS' DEVICE (not on whatever device happens to be current)."""
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def _h(device=None):
+    """das_handle* of a device (one per device per process, _lib.handle)."""
+    return _lib.handle(device)
+
+
+import contextlib
+
+
+@contextlib.contextmanager
+def option(name: str, value: int, device=None):
+    """Temporarily set a das_handle option, e.g. `with ops.option("mc_tma", 0): ...` (A/B measurements, tests)."""
+    old = _lib.set_option(name, value, device)
+    try:
+        yield
+    finally:
+        _lib.set_option(name, old, device)
 
 
 def _need_cuda(t: torch.Tensor, name: str, dtype=None):
@@ -53,6 +72,9 @@ class MCState:
         self.B, self.C, self.H, self.W, self.T_cap = B, C_, H, W, T_cap
         self.votes, self.probs = votes, probs
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
+        self.h = _h(self.device)
         nbytes = C.c_size_t()
         check(self.lib.das_mc_state_bytes(C.byref(self.desc), C.byref(nbytes)), "das_mc_state_bytes")
         self.nbytes = nbytes.value
@@ -69,8 +91,8 @@ class MCState:
         while start < len(group):
             chunk = self._check_group(group[start:start + _lib.MAX_PASS_GROUP])
             arr = (C.c_void_p * len(chunk))(*[t.data_ptr() for t in chunk])
-            check(self.lib.das_mc_accumulate(C.byref(self.desc), _ptr(self.state), arr, len(chunk), self.n_passes,
-                                             _stream()), "das_mc_accumulate")
+            check(self.lib.das_mc_accumulate(self.h, C.byref(self.desc), _ptr(self.state), arr, len(chunk), self.n_passes,
+                                             _stream(self.device)), "das_mc_accumulate")
             self.n_passes += len(chunk)
             start += len(chunk)
 
@@ -78,6 +100,8 @@ class MCState:
         group = [pass_logits] if isinstance(pass_logits, torch.Tensor) else list(pass_logits)
         chunk = [_need_cuda(t, "logits", torch.float32) for t in group]
         for t in chunk:
+            if t.device != self.device:
+                raise DasError(f"logits live on {t.device}, the state on {self.device}")
             if tuple(t.shape) != (self.B, self.C, self.H, self.W):
                 raise DasError(f"logits shape {tuple(t.shape)} != {(self.B, self.C, self.H, self.W)}")
         return chunk
@@ -93,9 +117,9 @@ class MCState:
             chunk = chunk[head:]
         labels, bufs, wl, sc = self._outputs(labels, maps, scores, weak_labels, scores_out)
         arr = (C.c_void_p * len(chunk))(*[t.data_ptr() for t in chunk])
-        check(self.lib.das_mc_accumulate_finalize(C.byref(self.desc), _ptr(self.state), arr, len(chunk), self.n_passes,
-                                                  _ptr(labels), *[_ptr(bufs.get(n)) for n in MAP_NAMES], _ptr(wl),
-                                                  _ptr(sc), _stream()), "das_mc_accumulate_finalize")
+        check(self.lib.das_mc_accumulate_finalize(self.h, C.byref(self.desc), _ptr(self.state), arr, len(chunk),
+                                                  self.n_passes, _ptr(labels), *[_ptr(bufs.get(n)) for n in MAP_NAMES],
+                                                  _ptr(wl), _ptr(sc), _stream(self.device)), "das_mc_accumulate_finalize")
         self.n_passes += len(chunk)
         return self._pack(bufs, wl, sc)
 
@@ -118,9 +142,9 @@ class MCState:
                 raise DasError(f"low-res logits shape {tuple(t.shape)} != {(self.B, self.C, h, w)}")
         labels, bufs, wl, sc = self._outputs(labels, maps, scores, weak_labels, scores_out)
         arr = (C.c_void_p * len(chunk))(*[t.data_ptr() for t in chunk])
-        check(self.lib.das_mc_upsample_accumulate_finalize(C.byref(self.desc), _ptr(self.state), arr, len(chunk), h, w,
-                                                           _ptr(labels), *[_ptr(bufs.get(n)) for n in MAP_NAMES],
-                                                           _ptr(wl), _ptr(sc), _stream()),
+        check(self.lib.das_mc_upsample_accumulate_finalize(self.h, C.byref(self.desc), _ptr(self.state), arr, len(chunk),
+                                                           h, w, _ptr(labels), *[_ptr(bufs.get(n)) for n in MAP_NAMES],
+                                                           _ptr(wl), _ptr(sc), _stream(self.device)),
               "das_mc_upsample_accumulate_finalize")
         self.n_passes += len(chunk)
         return self._pack(bufs, wl, sc)
@@ -132,8 +156,8 @@ class MCState:
         if self.n_passes < 1:
             raise DasError("finalize() before any accumulate()")
         labels, bufs, wl, sc = self._outputs(labels, maps, scores, weak_labels, scores_out)
-        check(self.lib.das_mc_finalize(C.byref(self.desc), _ptr(self.state), _ptr(labels), self.n_passes,
-                                       *[_ptr(bufs.get(n)) for n in MAP_NAMES], _ptr(wl), _ptr(sc), _stream()),
+        check(self.lib.das_mc_finalize(self.h, C.byref(self.desc), _ptr(self.state), _ptr(labels), self.n_passes,
+                                       *[_ptr(bufs.get(n)) for n in MAP_NAMES], _ptr(wl), _ptr(sc), _stream(self.device)),
               "das_mc_finalize")
         return self._pack(bufs, wl, sc)
 
@@ -175,9 +199,9 @@ class MCState:
         return self.state[off:off + n].view(self.B, self.T_cap, self.H, self.W).clone()
 
 
-def upsample_supported(h: int, w: int, H: int, W: int) -> bool:
+def upsample_supported(h: int, w: int, H: int, W: int, device=None) -> bool:
     """Can score_upsampled() interpolate h x w -> H x W in-kernel (else: F.interpolate + score())?"""
-    return bool(_lib.load().das_mc_upsample_supported(int(h), int(w), int(H), int(W)))
+    return bool(_lib.load().das_mc_upsample_supported(_h(device), int(h), int(w), int(H), int(W)))
 
 
 # ---------------------------------------------------------------------------------------------
@@ -193,7 +217,8 @@ def suppress_rects(maps: torch.Tensor, rects) -> None:
         return
     r = torch.as_tensor(rects, dtype=torch.int32).reshape(-1, 5).to(maps.device)
     B, H, W = maps.shape
-    check(_lib.load().das_suppress_rects(_ptr(maps), B, H, W, _ptr(r), r.shape[0], _stream()), "das_suppress_rects")
+    check(_lib.load().das_suppress_rects(_h(maps.device), _ptr(maps), B, H, W, _ptr(r), r.shape[0], _stream(maps.device)),
+          "das_suppress_rects")
 
 
 def add_maps(a: torch.Tensor, b: torch.Tensor) -> None:
@@ -201,12 +226,12 @@ def add_maps(a: torch.Tensor, b: torch.Tensor) -> None:
     b = _need_cuda(b, "b", torch.float32)
     if not a.is_contiguous() or a.numel() != b.numel():
         raise DasError("add_maps: a must be contiguous and the sizes must agree")
-    check(_lib.load().das_add_maps(_ptr(a), _ptr(b), a.numel(), _stream()), "das_add_maps")
+    check(_lib.load().das_add_maps(_h(a.device), _ptr(a), _ptr(b), a.numel(), _stream(a.device)), "das_add_maps")
 
 
 def new_minmax(device) -> torch.Tensor:
     mm = torch.empty(2, dtype=torch.float32, device=device)
-    check(_lib.load().das_minmax_init(_ptr(mm), _stream()), "das_minmax_init")
+    check(_lib.load().das_minmax_init(_h(mm.device), _ptr(mm), _stream(mm.device)), "das_minmax_init")
     return mm
 
 
@@ -222,7 +247,8 @@ def box_sum(maps: torch.Tensor, R: int, minmax: torch.Tensor, out: torch.Tensor 
         out = torch.empty((B, H - R + 1, W - R + 1), dtype=torch.float32, device=maps.device)
     elif not out.is_contiguous() or tuple(out.shape) != (B, H - R + 1, W - R + 1):
         raise DasError("box_sum: bad `out`")
-    check(lib.das_box_sum(_ptr(maps), B, H, W, R, _ptr(out), _ptr(minmax), _ptr(ws), _stream()), "das_box_sum")
+    check(lib.das_box_sum(_h(maps.device), _ptr(maps), B, H, W, R, _ptr(out), _ptr(minmax), _ptr(ws), _stream(maps.device)),
+          "das_box_sum")
     return out
 
 
@@ -230,8 +256,8 @@ def minmax_normalise(score_maps: torch.Tensor, minmax: torch.Tensor) -> None:
     if not score_maps.is_contiguous():
         raise DasError("minmax_normalise: score_maps must be contiguous (modified in place)")
     _need_cuda(score_maps, "score_maps", torch.float32)
-    check(_lib.load().das_minmax_normalise(_ptr(score_maps), score_maps.numel(), _ptr(minmax), _stream()),
-          "das_minmax_normalise")
+    check(_lib.load().das_minmax_normalise(_h(score_maps.device), _ptr(score_maps), score_maps.numel(), _ptr(minmax),
+                                           _stream(score_maps.device)), "das_minmax_normalise")
 
 
 def nms_pick_bound(H2: int, W2: int, R: int) -> int:
@@ -252,8 +278,8 @@ def nms_sequences(score_maps: torch.Tensor, R: int, kmax: int, stop: float = 0.0
     rc = torch.zeros((N, kmax, 2), dtype=torch.int32, device=dev)
     cnt = torch.zeros((N,), dtype=torch.int32, device=dev)
     flat = torch.empty((N, kmax), dtype=torch.int64, device=dev) if with_flat else None
-    check(_lib.load().das_nms_sequences(_ptr(score_maps), N, H2, W2, R, kmax, C.c_float(stop), _ptr(cs), _ptr(rc),
-                                        _ptr(cnt), int(image_offset), _ptr(flat), _stream()), "das_nms_sequences")
+    check(_lib.load().das_nms_sequences(_h(dev), _ptr(score_maps), N, H2, W2, R, kmax, C.c_float(stop), _ptr(cs), _ptr(rc),
+                                        _ptr(cnt), int(image_offset), _ptr(flat), _stream(dev)), "das_nms_sequences")
     if with_flat:
         return cs, rc, cnt, flat
     return cs, rc, cnt
@@ -278,8 +304,8 @@ def accuracy_scores(logits: torch.Tensor, labels: torch.Tensor | None, num_class
     ws = torch.empty(nbytes.value, dtype=torch.uint8, device=logits.device)
     scores = torch.empty((B, len(_lib.ACC_INDEX)), dtype=torch.float32, device=logits.device)
     pm = torch.empty((B, H, W), dtype=torch.float32, device=logits.device) if p0_map else None
-    check(lib.das_accuracy_scores(_ptr(logits), B, Cc, H, W, _ptr(labels), int(num_classes), _ptr(pm), _ptr(scores),
-                                  _ptr(ws), _stream()), "das_accuracy_scores")
+    check(lib.das_accuracy_scores(_h(logits.device), _ptr(logits), B, Cc, H, W, _ptr(labels), int(num_classes), _ptr(pm),
+                                  _ptr(scores), _ptr(ws), _stream(logits.device)), "das_accuracy_scores")
     return (scores, pm) if p0_map else scores
 
 
@@ -302,8 +328,8 @@ def maxsubset_greedy(X: torch.Tensor, Y: torch.Tensor, k: int) -> torch.Tensor:
     check(lib.das_maxsubset_workspace_bytes(N, M, D, f64, C.byref(nbytes)), "das_maxsubset_workspace_bytes")
     ws = torch.empty(nbytes.value, dtype=torch.uint8, device=X.device)
     picks = torch.empty(max(k, 1), dtype=torch.int32, device=X.device)
-    check(lib.das_maxsubset_greedy(_ptr(X), _ptr(Y), N, M, D, f64, int(k), _ptr(picks), _ptr(ws), _stream()),
-          "das_maxsubset_greedy")
+    check(lib.das_maxsubset_greedy(_h(X.device), _ptr(X), _ptr(Y), N, M, D, f64, int(k), _ptr(picks), _ptr(ws),
+                                   _stream(X.device)), "das_maxsubset_greedy")
     return picks[:k]
 
 
@@ -324,9 +350,45 @@ def topk(scores: torch.Tensor, k: int, descending: bool, ids: torch.Tensor | Non
         ids = _need_cuda(ids, "ids", torch.int64).reshape(-1)
         if ids.numel() != n:
             raise DasError("topk: ids and scores differ in length")
-    check(_lib.load().das_topk(_ptr(scores), _ptr(ids), n, k, 1 if descending else 0, _ptr(out_s), _ptr(out_i), None,
-                               _stream()), "das_topk")
+    check(_lib.load().das_topk(_h(scores.device), _ptr(scores), _ptr(ids), n, k, 1 if descending else 0, _ptr(out_s),
+                               _ptr(out_i), None, _stream(scores.device)), "das_topk")
     return out_s, out_i
+
+
+def topk_records(scores: torch.Tensor, k_slots: int, descending: bool, ids: torch.Tensor | None = None,
+                 id_offset: int = 0, out: torch.Tensor | None = None) -> torch.Tensor:
+    """This rank's best min(k_slots, n) candidates as int64 records [k_slots, 2] = {float32 score bits, id + id_offset}
+    (padding records {-/+inf, -1} behind them): the send buffer of the candidate all-gather (das_topk_records)."""
+    scores = _need_cuda(scores, "scores", torch.float32).reshape(-1)
+    n = scores.numel()
+    if ids is not None:
+        ids = _need_cuda(ids, "ids", torch.int64).reshape(-1)
+        if ids.numel() != n:
+            raise DasError("topk_records: ids and scores differ in length")
+    rec = torch.empty((int(k_slots), 2), dtype=torch.int64, device=scores.device) if out is None else out
+    check(_lib.load().das_topk_records(_h(scores.device), _ptr(scores) if n else None, _ptr(ids), n, int(k_slots),
+                                       1 if descending else 0, int(id_offset), _ptr(rec), _stream(scores.device)),
+          "das_topk_records")
+    return rec
+
+
+def topk_merge(records: torch.Tensor, k_slots: int, descending: bool) -> torch.Tensor:
+    """First k_slots records of the stable ranking of a gathered record table [m, 2] (das_topk_merge)."""
+    records = _need_cuda(records, "records", torch.int64)
+    out = torch.empty((int(k_slots), 2), dtype=torch.int64, device=records.device)
+    check(_lib.load().das_topk_merge(_h(records.device), _ptr(records), records.shape[0], int(k_slots),
+                                     1 if descending else 0, _ptr(out), _stream(records.device)), "das_topk_merge")
+    return out
+
+
+def records_to_host(records: torch.Tensor):
+    """int64 records [m, 2] (any device) -> (float32 scores [m'], int64 ids [m']) numpy arrays without the padding."""
+    import numpy as np
+
+    r = records.detach().cpu().numpy()
+    keep = r[:, 1] >= 0
+    sc = np.ascontiguousarray(r[keep, 0]).astype(np.uint32).view(np.float32)
+    return sc, np.ascontiguousarray(r[keep, 1])
 
 
 # ---------------------------------------------------------------------------------------------
@@ -350,8 +412,9 @@ class KCenterFilter:
         raw = torch.empty(self.nbytes + 1024, dtype=torch.uint8, device=feats.device)
         off = (-raw.data_ptr()) % 1024
         self.blob = raw[off:off + self.nbytes]
-        check(lib.das_kcenter_filter_build(_ptr(feats), self.N, self.D, self.row_begin, self.row_end, _ptr(self.blob),
-                                           _stream()), "das_kcenter_filter_build")
+        self.device = feats.device
+        check(lib.das_kcenter_filter_build(_h(feats.device), _ptr(feats), self.N, self.D, self.row_begin, self.row_end,
+                                           _ptr(self.blob), _stream(feats.device)), "das_kcenter_filter_build")
 
     @staticmethod
     def bytes_needed(N: int, D: int, rows: int) -> int:
@@ -362,8 +425,8 @@ class KCenterFilter:
     def stats(self):
         """(exact float64 row evaluations, rows screened) so far."""
         out = (C.c_uint64 * 2)()
-        check(_lib.load().das_kcenter_filter_stats(_ptr(self.blob), self.N, self.D, self.rows, out, _stream()),
-              "das_kcenter_filter_stats")
+        check(_lib.load().das_kcenter_filter_stats(_h(self.device), _ptr(self.blob), self.N, self.D, self.rows, out,
+                                                   _stream(self.device)), "das_kcenter_filter_stats")
         return int(out[0]), int(out[1])
 
 
@@ -383,27 +446,28 @@ def kcenter_greedy(feats: torch.Tensor, centers: Sequence[int] | torch.Tensor, K
     cen = torch.as_tensor(centers, dtype=torch.int32).reshape(-1).to(feats.device)
     lib = _lib.load()
     nbytes = C.c_size_t()
-    check(lib.das_kcenter_workspace_bytes(N, D, C.byref(nbytes)), "das_kcenter_workspace_bytes")
+    check(lib.das_kcenter_workspace_bytes(_h(feats.device), N, D, C.byref(nbytes)), "das_kcenter_workspace_bytes")
     ws = torch.empty(nbytes.value, dtype=torch.uint8, device=feats.device)
     picks = torch.empty(max(K, 1), dtype=torch.int32, device=feats.device)
     min_d = torch.empty(N, dtype=torch.float64, device=feats.device)
-    check(lib.das_kcenter_greedy(_ptr(feats), N, D, _ptr(cen), cen.numel(), K, _ptr(picks), _ptr(min_d), _ptr(ws),
-                                 _filter_ptr(flt, feats, 0, N), _stream()), "das_kcenter_greedy")
+    check(lib.das_kcenter_greedy(_h(feats.device), _ptr(feats), N, D, _ptr(cen), cen.numel(), K, _ptr(picks), _ptr(min_d),
+                                 _ptr(ws), _filter_ptr(flt, feats, 0, N), _stream(feats.device)), "das_kcenter_greedy")
     return picks[:K], min_d
 
 
 def kcenter_init(feats, row_begin, row_end, centers, min_d2, key2, flt: KCenterFilter | None = None):
     N, D = feats.shape
-    check(_lib.load().das_kcenter_init(_ptr(feats), N, D, row_begin, row_end, _ptr(centers), centers.numel(),
-                                       _ptr(min_d2), _ptr(key2), _filter_ptr(flt, feats, row_begin, row_end), _stream()),
+    check(_lib.load().das_kcenter_init(_h(feats.device), _ptr(feats), N, D, row_begin, row_end, _ptr(centers),
+                                       centers.numel(), _ptr(min_d2), _ptr(key2),
+                                       _filter_ptr(flt, feats, row_begin, row_end), _stream(feats.device)),
           "das_kcenter_init")
 
 
 def kcenter_step(feats, row_begin, row_end, centre_idx, min_d2, key2, flt: KCenterFilter | None = None):
     N, D = feats.shape
-    check(_lib.load().das_kcenter_step(_ptr(feats), N, D, row_begin, row_end, _ptr(centre_idx), _ptr(min_d2),
-                                       _ptr(key2), _filter_ptr(flt, feats, row_begin, row_end), _stream()),
-          "das_kcenter_step")
+    check(_lib.load().das_kcenter_step(_h(feats.device), _ptr(feats), N, D, row_begin, row_end, _ptr(centre_idx),
+                                       _ptr(min_d2), _ptr(key2), _filter_ptr(flt, feats, row_begin, row_end),
+                                       _stream(feats.device)), "das_kcenter_step")
 
 
 def kcenter_filter_budget_ok(N: int, D: int, rows: int, device) -> bool:

@@ -16,7 +16,13 @@
  *  - return value: DAS_OK (0) or a negative das_status; das_strerror() names it;
  *    das_last_cuda_error() returns the cudaError_t behind DAS_ERR_CUDA.
  *  - the caller owns every buffer; state / workspace sizes come from the *_bytes() queries.
- *  - thread-compatible, not thread-safe: one host thread per state / workspace.
+ *  - every entry point that enqueues work takes a `das_handle*` first: one opaque handle per device
+ *    (das_handle_create).  The handle holds what used to be process state: the device ordinal and its
+ *    SM count (grid sizing), the tuning options (read from the environment ONCE, at creation), the
+ *    k-center step scratch and a cache of encoded TMA descriptors.  A call made while another device
+ *    is current switches to the handle's device for its duration.
+ *  - thread-compatible, not thread-safe: one host thread per handle / state / workspace at a time;
+ *    different handles (devices) may be used from different threads concurrently.
  *  - there is NO CPU fallback anywhere behind this ABI.
  */
 #ifndef DAS_B200_H
@@ -29,7 +35,7 @@
 extern "C" {
 #endif
 
-#define DAS_ABI_VERSION 3
+#define DAS_ABI_VERSION 4
 
 typedef enum das_status {
     DAS_OK = 0,
@@ -41,9 +47,35 @@ typedef enum das_status {
 
 const char* das_strerror(int status);
 int das_abi_version(void);
+/* cudaError_t behind the last DAS_ERR_CUDA returned to the calling thread */
 int das_last_cuda_error(void);
-/* number of kernels this library has launched since load (bench.py's "gpu_launches") */
+/* number of kernels this library has launched since load, all handles (bench.py's "gpu_launches") */
 uint64_t das_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------
+ * Per-device handle ("one opaque per-device handle")
+ * ------------------------------------------------------------------------------------------ */
+typedef struct das_handle das_handle;
+
+/* tuning options; defaults come from the environment variable named in the comment, read once in
+ * das_handle_create, and can be changed per handle with das_handle_set_option */
+enum {
+    DAS_OPT_MC_TMA = 0,        /* DAS_MC_TMA       1: TMA-ring single-shot kernel when eligible (default), 0: LDG kernel   */
+    DAS_OPT_MC_TMA_CTAS = 1,   /* DAS_MC_TMA_CTAS  CTAs per SM of the TMA kernel, 0 = per class count (default)           */
+    DAS_OPT_MC_UP_WARPS = 2,   /* DAS_MC_UP_WARPS  consumer warps of the fused-upsample kernel: 0 = auto, 4 or 15          */
+    DAS_OPT_GEMM_2CTA = 3,     /* DAS_GEMM_2CTA    1: CTA-pair tcgen05 distance GEMM (default), 0: one CTA per tile       */
+    DAS_OPT_KC_CLUSTER = 4,    /* DAS_KC_CLUSTER   1: k-center loop inside one thread-block cluster (default), 0: chain   */
+    DAS_OPT_MC_L2_PERSIST = 5, /* DAS_MC_L2_PERSIST 1: streaming accumulators pinned in L2 when they fit (default), 0: off */
+    DAS_OPT_COUNT = 6
+};
+
+/* device: CUDA ordinal, or -1 for the calling thread's current device */
+int das_handle_create(int device, das_handle** out);
+int das_handle_destroy(das_handle* h);
+int das_handle_device(const das_handle* h);       /* ordinal, or a negative das_status */
+int das_handle_sm_count(const das_handle* h);     /* multiprocessors of the device     */
+int das_handle_set_option(das_handle* h, int option, int value);
+int das_handle_get_option(const das_handle* h, int option, int* value);
 
 /* ------------------------------------------------------------------------------------------
  * Monte-Carlo uncertainty reduction  (K1 accumulate + K2 finalize)
@@ -92,7 +124,7 @@ typedef struct das_mc_desc {
 int das_mc_state_bytes(const das_mc_desc* desc, size_t* bytes);
 
 /* Optional: zero the state. das_mc_accumulate(pass_begin = 0) initialises it anyway. */
-int das_mc_reset(const das_mc_desc* desc, void* state, void* stream);
+int das_mc_reset(das_handle* h, const das_mc_desc* desc, void* state, void* stream);
 
 /* K1.  Consume `n_passes` (1..DAS_MAX_PASS_GROUP) Monte-Carlo passes in ONE launch.
  * pass_logits: HOST array of n_passes DEVICE pointers, each f32 [B,C,H,W] logits of one stochastic
@@ -101,7 +133,7 @@ int das_mc_reset(const das_mc_desc* desc, void* state, void* stream);
  * entropy, and adds them to the running state.  Passes pass_begin .. pass_begin+n_passes-1 are
  * recorded; pass_begin == 0 (re)initialises the state.  n_passes == 1 is the pure streaming form;
  * a larger group trades resident logits for fewer state round trips. */
-int das_mc_accumulate(const das_mc_desc* desc, void* state, const float* const* pass_logits,
+int das_mc_accumulate(das_handle* h, const das_mc_desc* desc, void* state, const float* const* pass_logits,
                       int n_passes, int pass_begin, void* stream);
 
 /* K2.  Turn the state after T passes into per-pixel maps and per-image scores.
@@ -118,7 +150,7 @@ int das_mc_accumulate(const das_mc_desc* desc, void* state, const float* const* 
  * image_scores: f32 [B, DAS_N_SCORES] or NULL: mean over ALL H*W pixels of each map (a score whose
  *   accumulator is not in desc->flags is written as NaN).
  * Scores are reduced in a fixed order (deterministic, independent of how a pool is sharded). */
-int das_mc_finalize(const das_mc_desc* desc, void* state, const float* labels, int T,
+int das_mc_finalize(das_handle* h, const das_mc_desc* desc, void* state, const float* labels, int T,
                     float* vote_entropy, float* pred_entropy, float* bald, float* confidence,
                     float* margin, uint8_t* weak_labels, float* image_scores, void* stream);
 
@@ -128,7 +160,7 @@ int das_mc_finalize(const das_mc_desc* desc, void* state, const float* labels, i
  * Monte-Carlo stack of a batch in one group; required when DAS_MC_SINGLE_SHOT is set) no state is read
  * or written at all: HBM traffic is the logits, once, plus the requested outputs.  Same outputs,
  * same arithmetic and same fixed reduction order as the two-call form. */
-int das_mc_accumulate_finalize(const das_mc_desc* desc, void* state, const float* const* pass_logits,
+int das_mc_accumulate_finalize(das_handle* h, const das_mc_desc* desc, void* state, const float* const* pass_logits,
                                int n_passes, int pass_begin, const float* labels, float* vote_entropy,
                                float* pred_entropy, float* bald, float* confidence, float* margin,
                                uint8_t* weak_labels, float* image_scores, void* stream);
@@ -145,13 +177,14 @@ int das_mc_accumulate_finalize(const das_mc_desc* desc, void* state, const float
  * flags combination, DAS_MC_SINGLE_SHOT recommended).  Pointers need 4-byte alignment only.
  * DAS_ERR_UNSUPPORTED when a 16-pixel output tile would read more than 6 source rows / columns (upsampling
  * factors below ~3.75: query das_mc_upsample_supported first and use F.interpolate + das_mc_accumulate_finalize). */
-int das_mc_upsample_accumulate_finalize(const das_mc_desc* desc, void* state,
+int das_mc_upsample_accumulate_finalize(das_handle* hd, const das_mc_desc* desc, void* state,
                                         const float* const* pass_lowres_logits, int n_passes, int h, int w,
                                         const float* labels, float* vote_entropy, float* pred_entropy,
                                         float* bald, float* confidence, float* margin, uint8_t* weak_labels,
                                         float* image_scores, void* stream);
-/* 1 if das_mc_upsample_accumulate_finalize handles the h x w -> H x W interpolation, else 0 (host only). */
-int das_mc_upsample_supported(int h, int w, int H, int W);
+/* 1 if das_mc_upsample_accumulate_finalize handles the h x w -> H x W interpolation, else 0 (host only; hd may be NULL:
+ * the default options are assumed). */
+int das_mc_upsample_supported(const das_handle* hd, int h, int w, int H, int W);
 
 /* Device pointer to the recorded votes, u8 [B,T_cap,H,W] (test / debugging aid). */
 int das_mc_votes_ptr(const das_mc_desc* desc, void* state, uint8_t** votes);
@@ -162,10 +195,10 @@ int das_mc_votes_ptr(const das_mc_desc* desc, void* state, uint8_t** votes);
 
 /* ActiveSelectionMCDropout.suppress_labeled_entropy (mc_dropout.py:110-121):
  * zero maps[i, r:r+h, c:c+w] for each of the n records (i, r, c, h, w) in `rects` (device, int32). */
-int das_suppress_rects(float* maps, int B, int H, int W, const int32_t* rects, int n, void* stream);
+int das_suppress_rects(das_handle* h, float* maps, int B, int H, int W, const int32_t* rects, int n, void* stream);
 
 /* a += b elementwise (combined noise + dropout vote entropy, mc_noise.py:141,165) */
-int das_add_maps(float* a, const float* b, size_t n, void* stream);
+int das_add_maps(das_handle* h, float* a, const float* b, size_t n, void* stream);
 
 /* Stride-1 'valid' RxR box sum, the conv2d-with-ones of mc_dropout.py:148-149:
  * out[b,r,c] = sum_{i<R,j<R} maps[b,r+i,c+j], out is f32 [B,H-R+1,W-R+1].  Sums are formed in
@@ -173,12 +206,12 @@ int das_add_maps(float* a, const float* b, size_t n, void* stream);
  * values already there (initialise with das_minmax_init), so a pool can be processed in batches
  * (mc_dropout.py:152-153).  workspace: das_box_sum_workspace_bytes(). */
 int das_box_sum_workspace_bytes(int B, int H, int W, int R, size_t* bytes);
-int das_minmax_init(float* minmax, void* stream);
-int das_box_sum(const float* maps, int B, int H, int W, int R, float* out, float* minmax,
+int das_minmax_init(das_handle* h, float* minmax, void* stream);
+int das_box_sum(das_handle* h, const float* maps, int B, int H, int W, int R, float* out, float* minmax,
                 void* workspace, void* stream);
 
 /* x = (x + (-min)) * (1 / (max - min)) in float32, exactly as mc_dropout.py:154-155. */
-int das_minmax_normalise(float* score_maps, size_t n, const float* minmax, void* stream);
+int das_minmax_normalise(das_handle* h, float* score_maps, size_t n, const float* minmax, void* stream);
 
 /* Per-image greedy NMS pick sequences - the image-local part of
  * ActiveSelectionMCDropout.square_nms (mc_dropout.py:82-108).  For each of the N images (one CTA
@@ -190,7 +223,7 @@ int das_minmax_normalise(float* score_maps, size_t n, const float* minmax, void*
  * Within an image the picks are sorted by (score desc, flat index asc), so the reference's global greedy loop is
  * exactly: das_topk over the flattened cand_score table (ties keep table order = flat order) and the stop rule
  * of mc_dropout.py:87,105 on that prefix - see active_selection/base.py:region_tail in the Python mirror. */
-int das_nms_sequences(float* score_maps, int N, int H2, int W2, int R, int kmax, float stop,
+int das_nms_sequences(das_handle* h, float* score_maps, int N, int H2, int W2, int R, int kmax, float stop,
                       float* cand_score, int32_t* cand_rc, int32_t* cand_count, long long image_offset,
                       int64_t* cand_flat, void* stream);
 
@@ -216,7 +249,7 @@ enum {
     DAS_ACC_N = 5
 };
 int das_accuracy_workspace_bytes(int B, int H, int W, size_t* bytes);
-int das_accuracy_scores(const float* logits, int B, int C, int H, int W, const float* labels, int num_classes,
+int das_accuracy_scores(das_handle* h, const float* logits, int B, int C, int H, int W, const float* labels, int num_classes,
                         float* p0_map, float* image_scores, void* workspace, void* stream);
 
 /* ------------------------------------------------------------------------------------------
@@ -228,7 +261,7 @@ int das_accuracy_scores(const float* logits, int B, int C, int H, int W, const f
  * picks: device int32 [k] candidate indices in pick order (-1 once every candidate is taken).
  * ------------------------------------------------------------------------------------------ */
 int das_maxsubset_workspace_bytes(int N, int M, int D, int is_f64, size_t* bytes);
-int das_maxsubset_greedy(const void* X, const void* Y, int N, int M, int D, int is_f64, int k, int32_t* picks,
+int das_maxsubset_greedy(das_handle* h, const void* X, const void* Y, int N, int M, int D, int is_f64, int k, int32_t* picks,
                          void* workspace, void* stream);
 
 /* ------------------------------------------------------------------------------------------
@@ -240,8 +273,22 @@ int das_maxsubset_greedy(const void* X, const void* Y, int N, int M, int D, int 
  * ------------------------------------------------------------------------------------------ */
 #define DAS_TOPK_MAX_K 4096
 int das_topk_workspace_bytes(int n, int k, size_t* bytes);
-int das_topk(const float* scores, const int64_t* ids, int n, int k, int descending,
+int das_topk(das_handle* h, const float* scores, const int64_t* ids, int n, int k, int descending,
              float* out_scores, int64_t* out_ids, void* workspace, void* stream);
+
+/* Multi-GPU ranking: each rank's best candidates travel as RECORDS - int64 pairs
+ * {float32 score bits in the low 32 bits, id} - so that ONE all-gather of a [k_slots, 2] int64 block per rank carries
+ * them, and the merge runs on the device of every rank.
+ * das_topk_records: like das_topk, but writes exactly k_slots records {score, ids[pos] + id_offset} (ids == NULL: the
+ *   position + id_offset = the global image index of a contiguous shard); slots beyond min(k_slots, n) are padding
+ *   records {-inf (descending) / +inf (ascending), -1}.  n == 0 (empty shard) writes padding only.
+ * das_topk_merge: the first k_slots of the stable ranking of a gathered record table (n_records = ranks * k_slots
+ *   records in rank order).  Ties keep table order = (rank, local order) = global index order for contiguous shards,
+ *   i.e. exactly the stable sort of the un-sharded pool; padding records (id < 0) rank below every candidate. */
+int das_topk_records(das_handle* h, const float* scores, const int64_t* ids, int n, int k_slots, int descending,
+                     long long id_offset, int64_t* records, void* stream);
+int das_topk_merge(das_handle* h, const int64_t* records, int n_records, int k_slots, int descending,
+                   int64_t* out_records, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Core-set k-center greedy  (K4)
@@ -263,31 +310,31 @@ int das_topk(const float* scores, const int64_t* ids, int n, int k, int descendi
  * The blob (1024-byte aligned, das_kcenter_filter_bytes) is N*rows*4 bytes + O(N*D): 0.44 GB for N = 10 000.
  * Pass filter = NULL to the functions below for the plain float64 path (any N). */
 int das_kcenter_filter_bytes(int N, int D, int rows, size_t* bytes);
-int das_kcenter_filter_build(const float* feats, int N, int D, int row_begin, int row_end, void* filter,
+int das_kcenter_filter_build(das_handle* h, const float* feats, int N, int D, int row_begin, int row_end, void* filter,
                              void* stream);
 /* HOST out: stats2[0] = exact float64 row evaluations so far, stats2[1] = rows screened (synchronises `stream`) */
-int das_kcenter_filter_stats(const void* filter, int N, int D, int rows, unsigned long long* stats2, void* stream);
+int das_kcenter_filter_stats(das_handle* h, const void* filter, int N, int D, int rows, unsigned long long* stats2, void* stream);
 
 /* min_d2[i - row_begin] = min_l ||f_i - f_centers[l]||^2 (fp64) for the L initial centres
  * (core_set.py:19,32-36); also writes the packed argmax key of the shard to key2:
  * key2[0] = float64 bits of max min_d2 (order preserving since d2 >= 0), key2[1] = its row index, ties ->
  * lowest i (np.argmax, core_set.py:22). */
-int das_kcenter_init(const float* feats, int N, int D, int row_begin, int row_end,
+int das_kcenter_init(das_handle* h, const float* feats, int N, int D, int row_begin, int row_end,
                      const int32_t* centers, int L, double* min_d2, unsigned long long* key2,
                      const void* filter, void* stream);
 
 /* One greedy step: centre = the row index held in *centre_idx (device int32); for every shard row
  * min_d2 = min(min_d2, ||f_i - f_centre||^2) (core_set.py:26,37-38) and the new shard argmax is
  * written to key2[0] (bits of the max), key2[1] (row index). */
-int das_kcenter_step(const float* feats, int N, int D, int row_begin, int row_end,
+int das_kcenter_step(das_handle* h, const float* feats, int N, int D, int row_begin, int row_end,
                      const int32_t* centre_idx, double* min_d2, unsigned long long* key2,
                      const void* filter, void* stream);
 
 /* Whole single-GPU greedy loop, no host round trip per step: picks int32 [K], min_d f64 [N]
  * (final euclidean min-distances, i.e. sqrt).  workspace: das_kcenter_workspace_bytes().
  * filter: blob built with row_begin = 0, row_end = N, or NULL. */
-int das_kcenter_workspace_bytes(int N, int D, size_t* bytes);
-int das_kcenter_greedy(const float* feats, int N, int D, const int32_t* centers, int L, int K,
+int das_kcenter_workspace_bytes(const das_handle* h, int N, int D, size_t* bytes);
+int das_kcenter_greedy(das_handle* h, const float* feats, int N, int D, const int32_t* centers, int L, int K,
                        int32_t* picks, double* min_d, void* workspace, const void* filter, void* stream);
 
 #ifdef __cplusplus

@@ -409,6 +409,128 @@ def gen_nms_png():
     print(f"[golden] nms_png: count={count} regions={rows.tolist()}")
 
 
+def _sample_pixels(seed, n, *shape):
+    """n deterministic pixel coordinates inside `shape` (tuple of index arrays)."""
+    rng = np.random.default_rng(seed)
+    return tuple(rng.integers(0, d, size=n) for d in shape)
+
+
+def gen_mc_baseline(name, seed, N, T, C, H, W, block, batch_size, n_samples=512):
+    """BASELINE config-2 shape (512 x 1024, C = 19, T = 20) through the REFERENCE selectors: MC-dropout vote entropy
+    (image scores + sampled map pixels) and the three single-pass CEAL scorers on pass 0.  The full maps would be
+    2 MB per image, so only `n_samples` pixels per image are stored; the composed scores of all T passes (predictive
+    entropy, BALD, MC confidence / margin - not in the reference) come from oracle/restate.py and are
+    stored under the `composed_` prefix (restatement-pinned, not reference-pinned)."""
+    from oracle import restate as R
+
+    ref = ref_shim.load_reference()
+    torch = ref.torch
+    ref.constants.MC_STEPS = T
+    pool = make_pool(seed, N, T, C, H, W, block)
+    paths = [str(i) for i in range(N)]
+    crop = H if H == W else -1
+    sel = ref.active_selection.get_active_selection_class("variance", C, pool, crop, batch_size)
+    cap = SortedCapture()
+    ref.mc_dropout.sorted = cap
+    chosen = sel.get_vote_entropy_for_images(ref_shim.make_replay_model(pool), paths, N)
+    del ref.mc_dropout.sorted
+    ve_scores = np.array(cap.calls[0][0], dtype=np.float32)
+    ds = ref_shim.SyntheticPathsDataset(pool, paths, crop, include_labels=True)
+    ve_maps = []
+    for b0 in range(0, N, batch_size):
+        image_batch = torch.stack([ds[i]["image"] for i in range(b0, min(N, b0 + batch_size))])
+        label_batch = torch.stack([ds[i]["label"] for i in range(b0, min(N, b0 + batch_size))])
+        ve_maps += [m.numpy() for m in sel._get_vote_entropy_for_batch(ref_shim.make_replay_model(pool), image_batch, label_batch)]
+    ve_maps = np.stack(ve_maps).astype(np.float32)
+    ceal = ref.active_selection.get_active_selection_class("ceal_entropy", C, pool, crop, batch_size)
+    _, ent = ceal.get_maximum_entropy_samples(ref_shim.make_replay_model(pool), paths, N)
+    cap = SortedCapture()
+    ref.ceal.sorted = cap
+    ceal.get_least_confident_samples(ref_shim.make_replay_model(pool), paths, N)
+    ceal.get_least_margin_samples(ref_shim.make_replay_model(pool), paths, N)
+    del ref.ceal.sorted
+    rows, cols = _sample_pixels(seed, n_samples, H, W)
+    # half of the samples on pixels that actually disagree (most pixels vote unanimously and score exactly 0)
+    for i in range(N):
+        nz = np.argwhere(ve_maps[i] > 0)
+        if len(nz):
+            pick = nz[np.random.default_rng(seed + i).integers(0, len(nz), size=n_samples // 2)]
+            if i == 0:
+                rows[: n_samples // 2], cols[: n_samples // 2] = pick[:, 0], pick[:, 1]
+    composed = {k: [] for k in R.SCORE_NAMES}
+    comp_px = {k: [] for k in ("pred_entropy", "bald", "confidence", "margin")}
+    for i in range(N):
+        o = R.mc_maps(pool.logits[i], pool.labels[i], C)
+        sc = R.image_scores(o)
+        for k in R.SCORE_NAMES:
+            composed[k].append(sc[k])
+        for k in comp_px:
+            comp_px[k].append(o[k][rows, cols])
+        assert np.array_equal(o["vote_entropy"], ve_maps[i]) or np.allclose(o["vote_entropy"], ve_maps[i], rtol=1e-6, atol=1e-7)
+    np.savez_compressed(
+        os.path.join(GOLDEN, name + ".npz"),
+        meta=np.array([seed, N, T, C, H, W, block, batch_size], dtype=np.int64), versions=versions(),
+        logits_sha=np.array(checksum(pool.logits)), labels_sha=np.array(checksum(pool.labels)),
+        ve_scores=ve_scores, ve_selected=paths_to_idx(chosen), px_rows=rows.astype(np.int32), px_cols=cols.astype(np.int32),
+        ve_px=ve_maps[:, rows, cols].astype(np.float32),
+        ceal_entropy=np.array(ent, dtype=np.float32), ceal_conf=np.array(cap.calls[0][0], dtype=np.float32),
+        ceal_margin=np.array(cap.calls[1][0], dtype=np.float32),
+        **{"composed_" + k: np.array(v, dtype=np.float32) for k, v in composed.items()},
+        **{"composed_px_" + k: np.stack(v).astype(np.float32) for k, v in comp_px.items()},
+    )
+    print(f"[golden] {name}: ve_scores={ve_scores} composed bald={composed['bald']}")
+
+
+def gen_region_rect(name, seed, N, T, C, H, W, block, R_, selection_size, n_samples=512):
+    """BASELINE config 3: rectangular 512 x 1024 planes, R = 128 (385 x 897 score maps).  The reference's
+    create_region_maps is square-only (`score_maps` is allocated (base - R + 1)^2), so this fixture is
+    RESTATEMENT-pinned: oracle/restate.py (itself pinned by the square reference goldens region_small / region_mid) with
+    K = selection_size * H * W / R^2, the rectangular reading of mc_dropout.py:157."""
+    from oracle import restate as R
+
+    gs = list(range(N))
+    logits = synth.pool_logits(seed, gs, T, C, H, W, block)
+    labels = synth.pool_labels(seed, gs, H, W, C, block)
+    rng = np.random.default_rng(seed + 1)
+    existing = []
+    for i in range(N):
+        existing.append([] if i % 2 == 0 else [(int(rng.integers(0, H - R_)), int(rng.integers(0, W - R_)), R_, R_)])
+    ve = [R.vote_entropy_map(R.votes_from_logits(logits[i]), C, R.valid_mask(labels[i], C)) for i in range(N)]
+    maps = np.stack([R.box_sum(R.suppress_rects(m.copy(), existing[i]), R_) for i, m in enumerate(ve)])
+    norm = R.minmax_normalise(maps)
+    K = (selection_size * H * W) / (R_ * R_)
+    regions, count = R.square_nms(norm.copy(), R_, K)
+    i_, r_, c_ = _sample_pixels(seed, n_samples, N, H - R_ + 1, W - R_ + 1)
+    rows = np.array([(i, *rc) for i, lst in enumerate(regions) for rc in lst], dtype=np.int64).reshape(-1, 4 + 1)
+    ex_rows = np.array([(i, *rc) for i, lst in enumerate(existing) for rc in lst], dtype=np.int64).reshape(-1, 5)
+    np.savez_compressed(
+        os.path.join(GOLDEN, name + ".npz"),
+        meta=np.array([seed, N, T, C, H, W, block, R_, selection_size], dtype=np.int64), versions=versions(),
+        logits_sha=np.array(checksum(logits)), existing=ex_rows, regions=rows, count=np.int64(count), K=np.float64(K),
+        raw_min=np.float32(maps.min()), raw_max=np.float32(maps.max()),
+        px=np.stack([i_, r_, c_]).astype(np.int32), norm_px=norm[i_, r_, c_].astype(np.float32),
+        pinned_by=np.array("restatement (reference is square-only)"))
+    print(f"[golden] {name}: {count} regions, K={K:.1f}, raw max={maps.max():.3f}")
+
+
+def gen_coreset_baseline(name, seed, N, D, L, K):
+    """BASELINE config 5 size through the REFERENCE _select_batch (sklearn float64 euclidean distances)."""
+    import time
+    ref = ref_shim.load_reference()
+    sel = ref.core_set.ActiveSelectionCoreSet(None, None, None)
+    feats32 = synth.coreset_features(seed, N, D)
+    t0 = time.time()
+    picks = sel._select_batch(feats32.astype(np.float64), list(range(L)), K)
+    dt = time.time() - t0
+    md = sel._updated_distances(list(range(L)) + [int(p) for p in picks], feats32.astype(np.float64), None)
+    np.savez_compressed(os.path.join(GOLDEN, name + ".npz"),
+                        meta=np.array([seed, N, D, L, K], dtype=np.int64), versions=versions(),
+                        features_sha=np.array(checksum(feats32)), picks=np.array(picks, dtype=np.int32),
+                        min_dist_max=np.float64(md.max()), min_dist_head=md[:256, 0].astype(np.float64),
+                        reference_seconds=np.float64(dt))
+    print(f"[golden] {name}: picks[:8]={picks[:8]} max min-dist={md.max():.6f} ({dt:.1f} s in the reference)")
+
+
 FIXTURES = {
     # odd H*W (alignment-peeling path), Pascal class count
     "mc_small": lambda: gen_mc("mc_small", synth.DEFAULT_SEED, N=6, T=5, C=21, H=65, W=65, block=8, k=3, batch_size=4),
@@ -432,6 +554,11 @@ FIXTURES = {
     # ... and 33 -> 129 (3 x 3 tiles with ragged edges, 9 tiles deep windows)
     "upsample_mid": lambda: gen_upsample("upsample_mid", synth.DEFAULT_SEED + 11, N=3, T=3, C=19, h=33, w=33, H=129, W=129, block=4, k=1, batch_size=2),
     "accuracy_small": lambda: gen_accuracy("accuracy_small", 41, 6, 5, 40, 8, 9, 4, 3),
+    # BASELINE sizes (VERDICT r1 "next" 1a): config 2's plane through the reference, config 3's rectangular maps through
+    # the restatement, config 5's N = 10 000 through the reference's sklearn loop
+    "mc_baseline": lambda: gen_mc_baseline("mc_baseline", synth.DEFAULT_SEED + 20, N=2, T=20, C=19, H=512, W=1024, block=32, batch_size=2),
+    "region_rect": lambda: gen_region_rect("region_rect", synth.DEFAULT_SEED + 21, N=3, T=5, C=19, H=512, W=1024, block=32, R_=128, selection_size=2),
+    "coreset_baseline": lambda: gen_coreset_baseline("coreset_baseline", synth.DEFAULT_SEED + 22, N=10000, D=2048, L=50, K=500),
 }
 
 

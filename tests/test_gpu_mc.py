@@ -225,12 +225,12 @@ def test_tma_ring_kernel_is_bit_identical_to_ldg_kernel(B, T, C, H, W, probs, vo
     maps = (["vote_entropy"] if votes else []) + [m for m in ops.MAP_NAMES if m != "vote_entropy"]
     outs = {}
     for tma in ("1", "0"):
-        monkeypatch.setenv("DAS_MC_TMA", tma)
-        n0 = _lib_launches()
-        st = ops.MCState(B, C, H, W, T, votes=votes, probs=probs, single_shot=True)
-        outs[tma] = st.score(dev, lab, maps=maps, scores=True, weak_labels=votes)
-        torch.cuda.synchronize()
-        assert _lib_launches() - n0 == 2
+        with ops.option("mc_tma", int(tma)):
+            n0 = _lib_launches()
+            st = ops.MCState(B, C, H, W, T, votes=votes, probs=probs, single_shot=True)
+            outs[tma] = st.score(dev, lab, maps=maps, scores=True, weak_labels=votes)
+            torch.cuda.synchronize()
+            assert _lib_launches() - n0 == 2
     for k in maps + (["weak_labels"] if votes else []):
         assert torch.equal(outs["1"][k], outs["0"][k]), k
     a, b = outs["1"]["scores"].cpu().numpy(), outs["0"]["scores"].cpu().numpy()
@@ -255,10 +255,10 @@ def test_tma_vs_ldg_bitwise_at_baseline_size(H, W, C, T, monkeypatch):
     maps = list(ops.MAP_NAMES)
     outs = {}
     for tma in ("1", "0"):
-        monkeypatch.setenv("DAS_MC_TMA", tma)
-        st = ops.MCState(B, C, H, W, T, votes=True, probs=True, single_shot=True)
-        outs[tma] = st.score(passes, labels, maps=maps, scores=True, weak_labels=True)
-        torch.cuda.synchronize()
+        with ops.option("mc_tma", int(tma)):
+            st = ops.MCState(B, C, H, W, T, votes=True, probs=True, single_shot=True)
+            outs[tma] = st.score(passes, labels, maps=maps, scores=True, weak_labels=True)
+            torch.cuda.synchronize()
     for k in maps + ["weak_labels"]:
         assert torch.equal(outs["1"][k], outs["0"][k]), k
     np.testing.assert_allclose(outs["1"]["scores"].cpu().numpy(), outs["0"]["scores"].cpu().numpy(), rtol=2e-6, atol=1e-7)
@@ -281,10 +281,167 @@ def test_every_class_count_family_tma_ldg_oracle(C, monkeypatch):
         lab = torch.from_numpy(labels).cuda()
         outs = {}
         for tma in ("1", "0"):
-            monkeypatch.setenv("DAS_MC_TMA", tma)
-            st = ops.MCState(B, C, H, W, T, votes=True, probs=True, single_shot=True)
-            outs[tma] = st.score(dev, lab, maps=list(ops.MAP_NAMES), scores=True)
-            torch.cuda.synchronize()
+            with ops.option("mc_tma", int(tma)):
+                st = ops.MCState(B, C, H, W, T, votes=True, probs=True, single_shot=True)
+                outs[tma] = st.score(dev, lab, maps=list(ops.MAP_NAMES), scores=True)
+                torch.cuda.synchronize()
         for k in ops.MAP_NAMES:
             assert torch.equal(outs["1"][k], outs["0"][k]), (C, H, W, k)
         check_against_oracle({k: v.cpu().numpy() for k, v in outs["1"].items()}, logits, labels)
+
+
+@pytest.mark.parametrize("H,W", [(8, 8), (5, 7), (16, 16), (16, 17)])
+@pytest.mark.parametrize("votes,probs", [(True, True), (True, False)])
+def test_signed_zero_ties_vote_like_torch_argmax(H, W, votes, probs):
+    """-0.0 == +0.0 for torch.argmax (mc_dropout.py:40): the first of them wins.  The kernels take the sign bit of
+    x_c + (0 - max) as "not a maximum", so a -0.0 logit next to a +0.0 maximum must still produce +0 (VERDICT r1 weak #2).
+    Shapes cover VEC = 4 / 2 / 1 LDG kernels, the TMA 3-D-map kernel (16 x 16) and the flat TMA kernel (16 x 17)."""
+    C, T = 7, 5
+    x = np.full((1, T, C, H, W), -3.0, dtype=np.float32)
+    nz, pz = np.float32(-0.0), np.float32(0.0)
+    x[0, 0, 0], x[0, 0, 1] = nz, pz                   # -0 before +0           -> 0
+    x[0, 1, 1], x[0, 1, 2] = pz, nz                   # +0 before -0           -> 1
+    x[0, 2, :] = nz                                   # every class -0         -> 0
+    x[0, 3, 3], x[0, 3, 5] = nz, pz                   # -0 at 3, +0 at 5       -> 3
+    x[0, 4, 2], x[0, 4, 4], x[0, 4, 6] = nz, nz, pz   # two -0 then +0         -> 2
+    x[0, 4, 0] = np.float32(-1e-30)                   # a tiny negative is NOT a maximum
+    want = torch.argmax(torch.from_numpy(x[0]), dim=1).numpy().astype(np.uint8)
+    assert want[:, 0, 0].tolist() == [0, 1, 0, 3, 2]
+    np.testing.assert_array_equal(R.votes_from_logits(x[0]), want)
+    labels = np.zeros((1, H, W), dtype=np.float32)
+    for fused, group in ((False, 1), (False, T), (True, T)):
+        res = run_gpu(x, labels, group, votes=votes, probs=probs, weak=True, fused=fused)
+        if "votes" in res:
+            np.testing.assert_array_equal(res["votes"][0, :T], want)
+        np.testing.assert_array_equal(res["weak_labels"][0], want[0])
+        check_against_oracle(res, x, labels, votes, probs)
+
+
+def _truth64(logits, C):
+    """float64 evaluation of the composed formulas (SURVEY Appendix A) for one image: [T,C,H,W] -> dict of [H,W]."""
+    x = logits.astype(np.float64)
+    e = np.exp(x - x.max(axis=1, keepdims=True))
+    p = e / e.sum(axis=1, keepdims=True)
+    pb = p.mean(axis=0)
+    ent = lambda q: -(q * np.log2(q + 1e-12)).sum(axis=-3)
+    part = np.partition(pb, C - 2, axis=0)
+    pe, ee = ent(pb), ent(p).mean(axis=0)
+    return {"pred_entropy": pe, "expected_entropy": ee, "bald": pe - ee, "confidence": pb.max(axis=0),
+            "margin": part[-1] - part[-2]}
+
+
+def _sweep_cases():
+    rng = np.random.default_rng(11)
+    H, W = 32, 64
+    n = H * W
+    cases = {}
+    # (a) the largest mean probability sweeps through 0.5, where MUFU.LG2 changes from a relative to an absolute bound
+    C, T = 19, 4
+    x = np.full((T, C, n), -40.0, dtype=np.float32)
+    x[:, 0] = 0.0
+    x[:, 1] = np.linspace(-0.5, 0.5, n, dtype=np.float32)[None] + rng.normal(0, 1e-3, (T, n)).astype(np.float32)
+    cases["top_prob_through_0.5"] = x.reshape(T, C, H, W)
+    # (b) the whole range of a dominant probability: 1e-6 .. 1 - 1e-6
+    x = np.full((T, C, n), -25.0, dtype=np.float32)
+    x[:, 3] = 0.0
+    x[:, 7] = np.linspace(-14.0, 14.0, n, dtype=np.float32)[None]
+    cases["top_prob_full_range"] = x.reshape(T, C, H, W)
+    # (c) C = 32 near-uniform: every probability close to 1/32, entropies close to 5 bits, margins close to 0
+    x = (rng.normal(0, 1e-3, (3, 32, n))).astype(np.float32) + np.float32(7.5)
+    cases["c32_near_uniform"] = x.reshape(3, 32, H, W)
+    # (d) T = 255 accumulations of wide-range logits (the streaming state in HBM)
+    base = rng.normal(0, 4.0, (17, 8, n)).astype(np.float32)
+    cases["t255_accumulation"] = base[np.arange(255) % 17].reshape(255, 8, H, W)
+    # (e) huge magnitudes: exp2 underflow of everything but the maximum
+    x = (rng.normal(0, 200.0, (T, C, n))).astype(np.float32)
+    cases["huge_magnitudes"] = x.reshape(T, C, H, W)
+    return cases
+
+
+@pytest.mark.parametrize("case", ["top_prob_through_0.5", "top_prob_full_range", "c32_near_uniform", "t255_accumulation",
+                                  "huge_magnitudes"])
+def test_approximation_error_sweep(case, capsys):
+    """ex2.approx / rcp.approx / lg2.approx (csrc/das_common.cuh) at their worst cases: max error of every softmax-derived
+    map against a float64 evaluation, for the streaming, the fused LDG and the TMA kernels.  north_star: 1e-5 relative;
+    the absolute floor is a few float32 ulp of the map's scale (entropies of C classes are <= log2 C)."""
+    x = _sweep_cases()[case]
+    T, C, H, W = x.shape
+    truth = _truth64(x, C)
+    oracle = R.mc_maps(x, None, C)
+    runs = {"streaming G=1" if T <= 32 else "streaming G=32": run_gpu(x[None], None, 1 if T <= 32 else 32, fused=False)}
+    if T <= 32:
+        runs["fused single shot (TMA)"] = run_gpu(x[None], None, T, fused=True)
+        ops = _ops()
+        with ops.option("mc_tma", 0):
+            runs["fused single shot (LDG)"] = run_gpu(x[None], None, T, fused=True)
+    scale = {"pred_entropy": np.log2(C), "expected_entropy": np.log2(C), "bald": np.log2(C), "confidence": 1.0, "margin": 1.0}
+    report = []
+    for kname, res in runs.items():
+        for name in ("pred_entropy", "bald", "confidence", "margin"):
+            got = res[name][0].astype(np.float64)
+            err = np.abs(got - truth[name])
+            rel = err / np.maximum(np.abs(truth[name]), 1e-2 * scale[name])
+            o_err = np.abs(oracle[name].astype(np.float64) - truth[name])
+            report.append(f"{case:>22} {kname:>24} {name:>13}: max abs {err.max():.2e} max rel(>1% of scale) {rel.max():.2e} "
+                          f"(float32 restatement: {o_err.max():.2e})")
+            # the bar, written out: 1e-5 relative + 4 float32 ulp of the map scale (BALD: a difference of two such maps)
+            atol = (8 if name == "bald" else 4) * 1.2e-7 * scale[name]
+            assert (err <= 1e-5 * np.abs(truth[name]) + atol).all(), report[-1]
+    with capsys.disabled():
+        print("\n" + "\n".join(report))
+
+
+def test_mc_noise_input_perturbation_is_observed():
+    """mc_noise.py:26-27: every pass sees image + N(0, 0.125) with FRESH noise.  A model whose logits are a fixed 1 x 1
+    projection of its input records what it was fed: sigma, mean, per-pass freshness, and the scorer's output must be the
+    oracle's on exactly those logits (VERDICT r1 weak #3)."""
+    from deep_active_semantic_segmentation_b200.active_selection import ActiveSelectionMCNoise, base
+    from deep_active_semantic_segmentation_b200 import constants
+    C, T, B, H, W = 6, 7, 2, 24, 40
+    proj = torch.linspace(-2, 2, C * 3).reshape(C, 3, 1, 1).cuda()
+
+    class Probe(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.drop = torch.nn.Dropout2d(0.25)
+            self.seen, self.out = [], []
+
+        def forward(self, x):
+            self.seen.append(x.detach().clone())
+            y = torch.nn.functional.conv2d(x, proj)
+            self.out.append(y.detach().clone())
+            return y
+
+    g = torch.Generator(device="cuda").manual_seed(3)
+    images = torch.rand((B, 3, H, W), generator=g, device="cuda")
+    labels = torch.zeros((B, H, W), device="cuda")
+    old_T = constants.MC_STEPS
+    constants.MC_STEPS = T
+    import sys
+    ref_constants = sys.modules.get("constants")
+    old_ref = getattr(ref_constants, "MC_STEPS", None) if ref_constants is not None else None
+    if old_ref is not None:
+        ref_constants.MC_STEPS = T
+    try:
+        sel = ActiveSelectionMCNoise(C, None, -1, B)
+        model = Probe().cuda().eval()
+        maps = sel._get_vote_entropy_for_batch_with_input_noise(model, images, labels)
+    finally:
+        constants.MC_STEPS = old_T
+        if old_ref is not None:
+            ref_constants.MC_STEPS = old_ref
+    assert len(model.seen) == T and len(maps) == B
+    noise = torch.stack([s - images for s in model.seen])              # [T,B,3,H,W]
+    n = noise[0].numel()
+    assert abs(float(noise.std()) - 0.125) < 0.125 * 0.02              # sigma of mc_noise.py:26 (T*n = 40k samples)
+    assert abs(float(noise.mean())) < 4 * 0.125 / np.sqrt(T * n)
+    for t in range(T):                                                # every pass is perturbed, and differently
+        assert abs(float(noise[t].std()) - 0.125) < 0.125 * 0.06
+        for u in range(t):
+            c = float((noise[t] * noise[u]).mean()) / 0.125 ** 2
+            assert abs(c) < 6 / np.sqrt(n), (t, u, c)
+    logits = torch.stack(model.out, dim=1).cpu().numpy()               # [B,T,C,H,W] as the scorer saw them
+    for b in range(B):
+        o = R.mc_maps(logits[b], labels[b].cpu().numpy(), C)
+        np.testing.assert_allclose(maps[b].cpu().numpy(), o["vote_entropy"], rtol=RTOL, atol=ATOL_MAP)
+    assert float(torch.stack(maps).max()) > 0                          # the noise does flip votes on this model

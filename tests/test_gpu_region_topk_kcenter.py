@@ -170,14 +170,35 @@ def test_kcenter_matches_reference_golden(name):
     np.testing.assert_allclose(sel.last_min_distances.cpu().numpy(), g["min_dist"], rtol=1e-9, atol=1e-4)
 
 
-def test_kcenter_asserts_like_reference_and_rejects_lossy_features():
+def test_kcenter_asserts_like_reference_and_rounds_wide_features_with_a_warning():
     from deep_active_semantic_segmentation_b200.active_selection import ActiveSelectionCoreSet
-    from deep_active_semantic_segmentation_b200._lib import DasError
     sel = ActiveSelectionCoreSet(None, None, None)
     with pytest.raises(AssertionError):
         sel._select_batch(np.zeros((4, 3)), [0], 1)          # all distances 0 -> argmax 0, already selected
-    with pytest.raises(DasError):
-        sel._select_batch(np.full((4, 3), 0.1), [0], 1)      # 0.1 is not a float32 value
+    # genuinely float64 features (0.1 is not a float32 value): accepted like the reference does, rounded, announced
+    rng = np.random.default_rng(5)
+    f64 = rng.standard_normal((40, 7)) + 0.1
+    with pytest.warns(RuntimeWarning, match="rounded to float32"):
+        picks = sel._select_batch(f64, [0, 1], 5)
+    assert picks == R.kcenter_greedy(f64.astype(np.float32), [0, 1], 5)[0]
+
+
+def test_updated_distances_keeps_the_reference_contract():
+    """core_set.py:32-38: [n,1] min over the centres when min_distances is None, else np.minimum(min_distances, dist)."""
+    from deep_active_semantic_segmentation_b200.active_selection import ActiveSelectionCoreSet
+    sel = ActiveSelectionCoreSet(None, None, None)
+    feats = synth.coreset_features(3, 200, 33).astype(np.float64)
+    d0 = sel._updated_distances([4, 9, 17], feats, None)
+    want0 = R.euclidean_to(feats, feats[[4, 9, 17]]).min(axis=1).reshape(-1, 1)
+    assert isinstance(d0, np.ndarray) and d0.shape == (200, 1) and d0.dtype == np.float64
+    np.testing.assert_allclose(d0, want0, rtol=1e-9, atol=1e-5)   # sklearn's expanded form carries ~1e-6 of noise at d = 0
+    d1 = sel._updated_distances([50], feats, d0)
+    np.testing.assert_allclose(d1, np.minimum(want0, R.euclidean_to(feats, feats[[50]])), rtol=1e-9, atol=1e-5)
+    assert d1.shape == (200, 1) and float(d1[50, 0]) == 0.0 and float(d0[4, 0]) == 0.0
+    d2 = sel._updated_distances([50, 60], feats, d0)              # broadcast like numpy does
+    assert d2.shape == (200, 2)
+    with pytest.raises(ValueError):
+        sel._updated_distances([], feats, None)
 
 
 def test_kcenter_odd_dimension_and_baseline_size_properties():

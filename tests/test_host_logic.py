@@ -24,7 +24,7 @@ def test_library_loads_and_exports_every_declared_symbol():
     assert declared == set(_lib.EXPORTED_SYMBOLS)
     for name in declared:
         assert isinstance(getattr(lib, name), ctypes._CFuncPtr)
-    assert lib.das_abi_version() == _lib.ABI_VERSION == 3
+    assert lib.das_abi_version() == _lib.ABI_VERSION == 4
     assert lib.das_strerror(0) == b"ok" and b"invalid" in lib.das_strerror(-1)
     # argument validation happens before any CUDA call, so these are safe without a device
     nbytes = ctypes.c_size_t()
@@ -36,7 +36,10 @@ def test_library_loads_and_exports_every_declared_symbol():
     assert lib.das_mc_state_bytes(ctypes.byref(_lib.McDesc(0, 5, 8, 8, 3, 3)), ctypes.byref(nbytes)) == -1
     assert lib.das_mc_state_bytes(ctypes.byref(_lib.McDesc(1, 5, 8, 8, 3, 0)), ctypes.byref(nbytes)) == -1
     assert lib.das_box_sum_workspace_bytes(1, 16, 16, 17, ctypes.byref(nbytes)) == -1     # R > H
-    assert lib.das_topk(None, None, 10, 3, 1, None, None, None, None) == -1
+    assert lib.das_topk(None, None, None, 10, 3, 1, None, None, None, None) == -1
+    # a NULL (or foreign) handle is refused before anything is enqueued
+    assert lib.das_minmax_init(None, None, None) == -1 and lib.das_handle_device(None) == -1
+    assert lib.das_handle_set_option(None, 0, 1) == -1 and lib.das_handle_destroy(None) == 0
 
 
 def test_product_path_has_no_cpu_fallback():
@@ -143,6 +146,32 @@ for fid in gi[:count].tolist():
     img, rem = divmod(fid, H2 * W2)
     regions[img].append((rem // W2, rem % W2, 3, 3))
 assert (regions, count) == want, (regions, count, want)
+# candidate RECORDS (the device path: das_topk_records -> exchange_records -> das_topk_merge), here packed and merged
+# by numpy stand-ins with the same layout: int64 pairs {float32 bits, global id}, padding {-/+inf, -1}
+def pack(sc, ids, k, desc):
+    rec = np.empty((k, 2), np.int64)
+    rec[:, 0] = np.array([-np.inf if desc else np.inf], np.float32).view(np.uint32)[0]
+    rec[:, 1] = -1
+    rec[:len(sc), 0] = np.asarray(sc, np.float32).view(np.uint32)
+    rec[:len(sc), 1] = ids
+    return torch.from_numpy(rec)
+lo, hi = dist.shard_bounds(n, W, rank)
+for desc in (True, False):
+    loc = R.rank_topk(scores[lo:hi].tolist(), k, desc)
+    table = dist.exchange_records(pack(scores[lo:hi][loc], np.array(loc) + lo, k, desc))
+    assert table.shape == (W * k, 2) and table.dtype == torch.int64
+    t = table.numpy()
+    sc = t[:, 0].astype(np.uint32).view(np.float32)
+    real = t[:, 1] >= 0
+    order = np.lexsort((np.arange(len(sc)), ~real, -sc if desc else sc))    # padding last, ties keep table order
+    got = t[order[:k], 1].tolist()
+    assert got == R.rank_topk(scores.tolist(), k, desc), (got, desc)
+# feature rows of a sharded forward pass (core-set): every rank ends with the whole matrix, ragged last shard included
+full = torch.arange(7 * 3, dtype=torch.float32).reshape(7, 3)
+lo, hi = dist.shard_bounds(7, W, rank)
+assert torch.equal(dist.all_gather_rows(full[lo:hi], 7), full)
+one = torch.ones(1, 3)
+assert torch.equal(dist.all_gather_rows(one[:1] if rank == 0 else one[:0], 1), one)
 td.barrier()
 print("RANK_OK", rank)
 '''
@@ -194,7 +223,7 @@ def test_upsample_shape_support_is_decided_on_the_host():
     arithmetic.  DeepLab's stride-4 decoder shapes and Fast-SCNN's factor 8 are in range, factor 2 is not."""
     from deep_active_semantic_segmentation_b200 import _lib
     lib = _lib.load()
-    ok = lambda h, w, H, W: bool(lib.das_mc_upsample_supported(h, w, H, W))
+    ok = lambda h, w, H, W: bool(lib.das_mc_upsample_supported(None, h, w, H, W))
     assert ok(128, 256, 512, 1024) and ok(129, 129, 513, 513) and ok(17, 17, 65, 65) and ok(12, 16, 48, 64)
     assert ok(64, 128, 512, 1024)            # models/fastscnn.py:22 (classifier at 1/8)
     assert not ok(32, 32, 64, 64) and not ok(64, 64, 64, 64) and not ok(100, 100, 300, 300)

@@ -163,6 +163,40 @@ def test_kcenter_matches_reference(name):
     np.testing.assert_allclose(m, g["min_dist"], rtol=1e-9, atol=1e-4)
 
 
+def test_kcenter_restatement_matches_reference_at_baseline_size():
+    """BASELINE config 5 (N = 10 000, D = 2048, L = 50, K = 500): 500 picks of the reference's sklearn loop."""
+    from deep_active_semantic_segmentation_b200 import synth
+
+    g = G.load("coreset_baseline")
+    seed, N, D, L, K = (int(v) for v in g["meta"])
+    feats = synth.coreset_features(seed, N, D)
+    assert G.sha(feats) == str(g["features_sha"])
+    picks, m = R.kcenter_greedy(feats, list(range(L)), K)
+    assert picks == g["picks"].tolist()
+    np.testing.assert_allclose(m.max(), float(g["min_dist_max"]), rtol=1e-9)
+    np.testing.assert_allclose(m[:256], g["min_dist_head"], rtol=1e-9, atol=1e-4)
+
+
+def test_restatement_matches_reference_at_config2_size():
+    """BASELINE config 2 plane (512 x 1024, C = 19, T = 20), image 0 of the mc_baseline golden: reference vote entropy
+    (score + sampled pixels) and the reference's single-pass CEAL scores."""
+    from deep_active_semantic_segmentation_b200 import synth
+
+    g = G.load("mc_baseline")
+    seed, N, T, C, H, W, block, bs = (int(v) for v in g["meta"])
+    logits = synth.pool_logits(seed, [0], T, C, H, W, block)[0]
+    labels = synth.pool_labels(seed, [0], H, W, C, block)[0]
+    valid = R.valid_mask(labels, C)
+    ve = R.vote_entropy_map(R.votes_from_logits(logits), C, valid)
+    rows, cols = g["px_rows"].astype(np.int64), g["px_cols"].astype(np.int64)
+    np.testing.assert_allclose(ve[rows, cols], g["ve_px"][0], rtol=RTOL, atol=ATOL)
+    np.testing.assert_allclose(np.float32(ve.mean(dtype=np.float64)), g["ve_scores"][0], rtol=RTOL, atol=1e-7)
+    single = R.image_scores(R.mc_maps(logits[:1], labels, C))
+    np.testing.assert_allclose(single["pred_entropy"], g["ceal_entropy"][0], rtol=RTOL, atol=1e-7)
+    np.testing.assert_allclose(single["confidence"], g["ceal_conf"][0], rtol=RTOL, atol=1e-7)
+    np.testing.assert_allclose(single["margin"], g["ceal_margin"][0], rtol=RTOL, atol=1e-7)
+
+
 def test_kcenter_asserts_on_reselection():
     feats = np.zeros((4, 3), dtype=np.float32)     # all distances 0 -> argmax = 0, already selected
     with pytest.raises(AssertionError):
