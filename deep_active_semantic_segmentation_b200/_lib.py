@@ -46,6 +46,7 @@ _PROTOTYPES = {
     "das_handle_destroy": (_i, [_h]),
     "das_handle_device": (_i, [_h]),
     "das_handle_sm_count": (_i, [_h]),
+    "das_handle_l2_info": (_i, [_h, C.POINTER(_sz), C.POINTER(_sz), C.POINTER(_sz)]),
     "das_handle_set_option": (_i, [_h, _i, _i]),
     "das_handle_get_option": (_i, [_h, _i, C.POINTER(_i)]),
     "das_mc_state_bytes": (_i, [C.POINTER(McDesc), C.POINTER(_sz)]),
@@ -154,6 +155,12 @@ def get_option(name: str, device=None) -> int:
     out = C.c_int()
     check(load().das_handle_get_option(handle(device), OPTIONS[name], C.byref(out)), "das_handle_get_option")
     return int(out.value)
+
+
+def l2_info(device=None) -> dict:
+    a, b, c = _sz(), _sz(), _sz()
+    check(load().das_handle_l2_info(handle(device), C.byref(a), C.byref(b), C.byref(c)), "das_handle_l2_info")
+    return {"l2_bytes": a.value, "persisting_max_bytes": b.value, "window_max_bytes": c.value}
 
 
 def launch_count() -> int:

@@ -62,6 +62,7 @@ class ActiveSelectionBase:
         self.pass_group_bytes = int(os.environ.get("DAS_PASS_GROUP_BYTES", 16 << 30))
         #: scores of the last pool pass, global image order (diagnostics / parity tests)
         self.last_scores = None
+        self.last_loader = None
 
     # -- pool iteration ------------------------------------------------------------------------
     def _shard(self, images):
@@ -74,7 +75,9 @@ class ActiveSelectionBase:
         (mc_dropout.py:131-132) - assembled in pinned memory by worker threads and copied asynchronously, so the
         batches arrive as CUDA tensors (prefetch.py)."""
         ds = _dataset_class()(self.env, images, self.crop_size, include_labels=include_labels)
-        return DeviceBatchLoader(ds, self.dataloader_batch_size)
+        #: the feeder of the last pool pass: .host_seconds / .batches / .path say what the host side of the pass cost
+        self.last_loader = DeviceBatchLoader(ds, self.dataloader_batch_size)
+        return self.last_loader
 
     # -- Monte-Carlo scoring of one batch --------------------------------------------------------
     def _group_size(self, T, per_pass_bytes):

@@ -31,12 +31,20 @@ class ActiveSelectionCoreSet(ActiveSelectionBase):
         #: per step (~60 us) when the rows of min_d are sharded.  True forces row sharding (larger pools, tests).
         self.shard_rows = "auto"
         self.replicated_rows_limit = 32768
+        self._budget_ok = {}
+        self.last_forward_rows = None
 
     def _make_filter(self, feats, lo, hi):
         n, d = feats.shape
         use = self.tensor_core_filter
         if use == "auto":
-            use = n * d >= (1 << 20) and ops.kcenter_filter_budget_ok(n, d, hi - lo, feats.device)
+            use = n * d >= (1 << 20)
+            if use:
+                # cudaMemGetInfo costs ~1 ms (a quarter of the whole selection at N = 10 000): asked once per shape
+                key = (n, d, hi - lo, str(feats.device))
+                if key not in self._budget_ok:
+                    self._budget_ok[key] = ops.kcenter_filter_budget_ok(n, d, hi - lo, feats.device)
+                use = self._budget_ok[key]
         return ops.KCenterFilter(feats, lo, hi) if use else None
 
     @staticmethod

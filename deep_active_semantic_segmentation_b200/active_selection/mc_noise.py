@@ -3,8 +3,8 @@
 Same vote-entropy reduction as MC-dropout; only the source of stochasticity differs:
 input noise N(0, 0.125) (mc_noise.py:26), the model's own feature noise (`set_noisy_features`,
 mc_noise.py:63,83) or dropout (mc_noise.py:88-91); the combined score adds two entropy maps
-per pixel (mc_noise.py:141-143,165-167).  The input noise is drawn on the device (the reference
-draws it with numpy on the host and uploads it every pass - SURVEY.md section 8(f) item 4).
+per pixel (mc_noise.py:141-143,165-167).  The input noise is drawn on the device, one `torch.normal(x, sigma)` per
+pass (the reference draws it with numpy on the host and uploads it every pass - SURVEY.md section 8(f) item 4).
 """
 from __future__ import annotations
 
@@ -32,7 +32,7 @@ class ActiveSelectionMCNoise(ActiveSelectionMCDropout):
 
     def _get_vote_entropy_for_batch_with_input_noise(self, model, image_batch, label_batch):
         def noisy_forward(x):
-            return model(x + torch.randn_like(x) * INPUT_NOISE_SIGMA)
+            return model(torch.normal(x, INPUT_NOISE_SIGMA))   # x + N(0, sigma), fresh per pass, ONE kernel
         return list(self._ve(noisy_forward, image_batch, label_batch)["vote_entropy"].unbind(0))
 
     def _feature_noise(self, model, image_batch, label_batch, maps=True):
@@ -69,7 +69,7 @@ class ActiveSelectionMCNoise(ActiveSelectionMCDropout):
         model.eval()
 
         def noisy_forward(x):
-            return model(x + torch.randn_like(x) * INPUT_NOISE_SIGMA)
+            return model(torch.normal(x, INPUT_NOISE_SIGMA))   # x + N(0, sigma), fresh per pass, ONE kernel
 
         col, lo = self._pool(images, lambda x, y: self._ve(noisy_forward, x, y, maps=False)["scores"][:, _VE])
         return self._rank(col, lo, images, selection_count, descending=True)
@@ -86,7 +86,7 @@ class ActiveSelectionMCNoise(ActiveSelectionMCDropout):
         model.eval()
 
         def noisy_forward(x):
-            return model(x + torch.randn_like(x) * INPUT_NOISE_SIGMA)
+            return model(torch.normal(x, INPUT_NOISE_SIGMA))   # x + N(0, sigma), fresh per pass, ONE kernel
 
         scores, lo = self._pool_scores(model, images, mc_steps(), votes=True, probs=True, forward=noisy_forward)
         allv = {name: self._all_scores(scores[:, j].contiguous(), len(images)) for name, j in SCORE_INDEX.items()}

@@ -79,6 +79,20 @@ struct HandleScope {
     ::das::HandleScope das_scope__(h);   \
     if (das_scope__.rc != DAS_OK) return das_scope__.rc
 
+// While alive, the kernels enqueued on `st` keep [base, base + bytes) resident in L2 (cudaAccessPolicyWindow with
+// hitProp = persisting, missProp = streaming; hitRatio scaled down when the range exceeds the persisting carve-out).
+// Used for the fp32 running state of the STREAMING Monte-Carlo reduction (das_mc_accumulate with G < T): the state is
+// re-read and re-written once per pass, and at B <= 2 images it fits the 126 MB L2, so the round trip stops there
+// instead of tripling the HBM traffic.  DAS_OPT_MC_L2_PERSIST = 0 (or a device without persisting L2) makes it a no-op.
+struct L2Window {
+    cudaStream_t st = nullptr;
+    bool active = false;
+    L2Window(das_handle* h, cudaStream_t stream, const void* base, size_t bytes);
+    ~L2Window();
+    L2Window(const L2Window&) = delete;
+    L2Window& operator=(const L2Window&) = delete;
+};
+
 // every kernel launch goes through this so that das_launch_count() is an honest count
 #define DAS_LAUNCH(kernel, grid, block, smem, stream, ...)                 \
     do {                                                                   \

@@ -87,6 +87,39 @@ const CUtensorMap* cached_tensor_map(das_handle* h, CUtensorMapDataType dtype, i
     return &slot.map;
 }
 
+L2Window::L2Window(das_handle* h, cudaStream_t stream, const void* base, size_t bytes) : st(stream) {
+    if (h == nullptr || !h->opt[DAS_OPT_MC_L2_PERSIST] || base == nullptr || bytes == 0) return;
+    if (h->l2_persist_max == 0 || h->l2_window_max == 0) return;
+    if (h->l2_persist_set < h->l2_persist_max) {  // carve the persisting share of L2 out once per handle
+        if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, h->l2_persist_max) != cudaSuccess) {
+            cudaGetLastError();
+            return;
+        }
+        h->l2_persist_set = h->l2_persist_max;
+    }
+    cudaStreamAttrValue v;
+    memset(&v, 0, sizeof(v));
+    const size_t win = bytes < h->l2_window_max ? bytes : h->l2_window_max;
+    v.accessPolicyWindow.base_ptr = const_cast<void*>(base);
+    v.accessPolicyWindow.num_bytes = win;
+    const double ratio = (double)h->l2_persist_set / (double)win;
+    v.accessPolicyWindow.hitRatio = ratio >= 1.0 ? 1.0f : (float)ratio;
+    v.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+    v.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+    if (cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &v) != cudaSuccess) {
+        cudaGetLastError();
+        return;
+    }
+    active = true;
+}
+
+L2Window::~L2Window() {
+    if (!active) return;
+    cudaStreamAttrValue v;
+    memset(&v, 0, sizeof(v));  // num_bytes = 0 disables the window for whatever is enqueued next on this stream
+    if (cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &v) != cudaSuccess) cudaGetLastError();
+}
+
 }  // namespace das
 
 using namespace das;
@@ -160,6 +193,14 @@ int das_handle_device(const das_handle* h) {
 }
 int das_handle_sm_count(const das_handle* h) {
     return (h == nullptr || h->magic != kDasHandleMagic) ? DAS_ERR_INVALID_ARG : h->num_sms;
+}
+
+int das_handle_l2_info(const das_handle* h, size_t* l2_bytes, size_t* persisting_max, size_t* window_max) {
+    if (h == nullptr || h->magic != kDasHandleMagic) return DAS_ERR_INVALID_ARG;
+    if (l2_bytes != nullptr) *l2_bytes = h->l2_bytes;
+    if (persisting_max != nullptr) *persisting_max = h->l2_persist_max;
+    if (window_max != nullptr) *window_max = h->l2_window_max;
+    return DAS_OK;
 }
 
 int das_handle_set_option(das_handle* h, int option, int value) {

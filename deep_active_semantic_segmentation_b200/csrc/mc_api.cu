@@ -98,6 +98,13 @@ static uintptr_t float_align(const das_mc_desc& d) {
 }
 static bool misaligned(const void* p, uintptr_t a) { return (reinterpret_cast<uintptr_t>(p) & (a - 1)) != 0; }
 
+// bytes of the fp32 accumulators at the head of the state (sum_p | sum_ent): what the streaming form round-trips per pass
+static size_t state_acc_bytes(const das_mc_desc& d) {
+    if (!(d.flags & DAS_MC_PROBS) || (d.flags & DAS_MC_SINGLE_SHOT)) return 0;
+    const size_t HW = (size_t)d.H * d.W;
+    return align_up((size_t)d.B * d.C * HW * sizeof(float), 256) + align_up((size_t)d.B * HW * sizeof(float), 256);
+}
+
 McLayout mc_layout(const das_mc_desc& d) {
     McLayout L;
     const size_t HW = (size_t)d.H * d.W;
@@ -333,6 +340,7 @@ int das_mc_accumulate(das_handle* h, const das_mc_desc* desc, void* state, const
     McAccParams p;
     rc = fill_acc_params(desc, state, pass_logits, n_passes, pass_begin, &p);
     if (rc != DAS_OK) return rc;
+    const L2Window keep(h, (cudaStream_t)stream, (desc->flags & DAS_MC_PROBS) ? state : nullptr, state_acc_bytes(*desc));
     return dispatch_accumulate(p, desc->B, acc_vec(*desc), desc->flags & (DAS_MC_VOTES | DAS_MC_PROBS),
                                (cudaStream_t)stream);
 }
@@ -349,6 +357,7 @@ int das_mc_finalize(das_handle* h, const das_mc_desc* desc, void* state, const f
                          mc_layout(*desc).blocks_per_image, &p);
     if (rc != DAS_OK) return rc;
     cudaStream_t st = (cudaStream_t)stream;
+    const L2Window keep(h, st, (desc->flags & DAS_MC_PROBS) ? state : nullptr, state_acc_bytes(*desc));
     rc = dispatch_finalize(p, desc->B, fin_vec(*desc), desc->flags & (DAS_MC_VOTES | DAS_MC_PROBS), st);
     if (rc != DAS_OK) return rc;
     return reduce_partials(desc, p, image_scores, st);
@@ -382,6 +391,8 @@ int das_mc_accumulate_finalize(das_handle* h, const das_mc_desc* desc, void* sta
         if (rc != DAS_OK) return rc;
         rc = dispatch_score_tma(tp, flags, h->opt[DAS_OPT_MC_TMA_CTAS], st);
     } else {
+        // the last group of a streamed batch reads the running state: keep it in L2 like das_mc_accumulate does
+        const L2Window keep(h, st, (pass_begin > 0 && (desc->flags & DAS_MC_PROBS)) ? state : nullptr, state_acc_bytes(*desc));
         rc = dispatch_score(q, desc->B, acc_vec(*desc), flags, st);
     }
     if (rc != DAS_OK) return rc;

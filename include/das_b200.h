@@ -74,6 +74,8 @@ int das_handle_create(int device, das_handle** out);
 int das_handle_destroy(das_handle* h);
 int das_handle_device(const das_handle* h);       /* ordinal, or a negative das_status */
 int das_handle_sm_count(const das_handle* h);     /* multiprocessors of the device     */
+/* L2 geometry the handle works with (bytes): total L2, the largest persisting carve-out, the largest access-policy window */
+int das_handle_l2_info(const das_handle* h, size_t* l2_bytes, size_t* persisting_max, size_t* window_max);
 int das_handle_set_option(das_handle* h, int option, int value);
 int das_handle_get_option(const das_handle* h, int option, int* value);
 

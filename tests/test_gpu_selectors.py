@@ -326,6 +326,27 @@ def test_device_batch_loader_yields_what_the_dataloader_yields():
     odd = list(DeviceBatchLoader(OddSet(), 4))
     assert len(odd) == 3 and odd[0]["name"] == ["img0", "img1", "img2", "img3"]
 
+    # items that live in pinned memory travel without a host copy (one async copy per item and field) - same batches
+    store = [{"image": torch.randn(3, 9, 7, generator=torch.Generator().manual_seed(i)).pin_memory(),
+              "label": torch.full((9, 7), float(i)).pin_memory()} for i in range(11)]
+
+    class PinnedSet(DictSet):
+        def __getitem__(self, i):
+            return store[i]
+
+    class MixedSet(DictSet):      # first item pinned, later ones pageable: staged item by item, still correct
+        def __getitem__(self, i):
+            return store[i] if i == 0 else {k: v.clone() for k, v in store[i].items()}
+
+    for ds, path in ((PinnedSet(), "direct"), (MixedSet(), "direct"), (DictSet(), "staged")):
+        loader = DeviceBatchLoader(ds, 4)
+        got = [{k: v.clone() for k, v in b.items()} for b in loader]
+        assert loader.path == path and loader.batches == 3 and loader.host_seconds > 0
+        want = list(DataLoader(ds, batch_size=4, shuffle=False, num_workers=0))
+        for g_, w_ in zip(got, want):
+            for k in w_:
+                torch.testing.assert_close(g_[k].cpu(), w_[k], rtol=0, atol=0)
+
 
 def test_region_selector_on_low_resolution_logits_equals_full_resolution():
     """create_region_maps with a model that returns low_res_x == create_region_maps on F.interpolate(low_res_x)
