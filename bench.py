@@ -64,6 +64,10 @@ def parse():
     return ap.parse_args()
 
 
+def peaks_sm_mhz():
+    return measured_peaks()[0].get("sm_max_mhz", 1965.0)
+
+
 def measured_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -706,9 +710,27 @@ def fused_upsample_variant(args, dev, steps=60):
     ms = e0.elapsed_time(e1) / steps
     out = {"value": round(B / ms * 1e3, 1), "unit": UNIT, "ms_per_step": round(ms, 4), "steps": steps,
            "kernel": "mc_score_up_kernel (fused bilinear upsample + K1 + K2)", "lowres": [h, w],
-           "bound": "issue slots / latency (not HBM)", "hbm_bytes_per_step": T * B * C * h * w * 4,
+           "hbm_bytes_per_step": T * B * C * h * w * 4,
            "fullres_bytes_avoided_per_step": 2 * T * B * C * H * W * 4,
            "note": "the network no longer writes T*B*C*H*W*4 bytes of interpolated logits and the scorer no longer reads them"}
+    # The kernel reads 16x fewer bytes than the resident-logits kernel (5 % of the HBM peak): its bounds are on chip.
+    #   MUFU: per pixel and pass C ex2 + 1 rcp + 1 lg2, per pixel C + 1 lg2 in the finalize; 16 MUFU lanes / clk / SM
+    #   issue: 378 warp instructions per pass and pixel pair in the pass loop (cuobjdump, C = 19) + finalize, 4 / clk / SM
+    sm_hz = float(peaks_sm_mhz()) * 1e6
+    n_sm = torch.cuda.get_device_properties(dev).multi_processor_count
+    px = B * H * W
+    mufu_ops = px * (T * (C + 2) + (C + 1)) if probs else 0
+    mufu_peak = n_sm * 16 * sm_hz
+    warp_instr = px / 64.0 * (T * 378.0 + 300.0) * (C / 19.0)        # pass loop (SASS count at C = 19) + ~300 per tile finalize
+    issue_peak = n_sm * 4 * sm_hz
+    out["roofline"] = {"bound": "mufu", "algorithmic_ops": int(mufu_ops), "peak_ops_per_s": mufu_peak,
+                       "achieved_ops_per_s": round(mufu_ops / (ms * 1e-3), 1), "frac": round(mufu_ops / (ms * 1e-3) / mufu_peak, 4),
+                       "mufu_bound_ms": round(mufu_ops / mufu_peak * 1e3, 4),
+                       "issue_bound": {"warp_instructions": int(warp_instr), "peak_warp_instr_per_s": issue_peak,
+                                       "frac": round(warp_instr / (ms * 1e-3) / issue_peak, 4),
+                                       "issue_bound_ms": round(warp_instr / issue_peak * 1e3, 4)},
+                       "note": "MUFU = 16 lanes/clk/SM at the maximum SM clock; the issue bound (one warp instruction per "
+                               "scheduler and clock) is the tighter one for this kernel: see profiles/r2_upsample_notes.md"}
     if args.no_e2e:
         return out
     # end to end: low-resolution logits of every pass from pinned host memory through the selector API

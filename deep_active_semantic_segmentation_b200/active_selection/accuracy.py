@@ -52,9 +52,28 @@ class ActiveSelectionAccuracy(ActiveSelectionBase):
         return self._select(scores, lo, "p0_sum" if mode == 'softmax' else "not_argmax_sum", images, selection_count)
 
     def get_adversarially_vulnarable_samples(self, model, images, selection_count):
-        # needs a backward pass through model.module.unet (accuracy.py:73-96): network side, not on the scoring path
-        raise NotImplementedError("gradient-norm selection runs a backward pass through the network; not part of the "
-                                  "B200 scoring path (SURVEY.md section 8, out of scope)")
+        """Image score = mean over ALL pixels of the per-pixel L2 norm (over the input channels) of
+        d sum(unet(z)) / dz at z = cat(softmax(segmentation logits), image), invalid pixels zeroed; descending
+        (accuracy.py:73-96).  The forward and the backward pass through `model.module.unet` are the network's own
+        (PyTorch, on the device - the reference detours through a host copy to detach z); the pool ranking is K3."""
+        model.eval()
+        lo, hi = self._shard(images)
+        chunks = []
+        for sample in self._loader(images[lo:hi], include_labels=True):
+            image_batch, label_batch = sample['image'].cuda(), sample['label'].cuda()
+            with torch.no_grad():
+                seg_logits, _ = model(image_batch)
+                z = torch.cat([torch.softmax(seg_logits, dim=1), image_batch], dim=1)
+            z.requires_grad_(True)
+            with torch.enable_grad():
+                head = model.module.unet(z)
+                head.backward(torch.ones_like(head))
+            norms = torch.linalg.vector_norm(z.grad, ord=2, dim=1)                       # [B,H,W]
+            norms = norms.masked_fill((label_batch < 0) | (label_batch >= self.num_classes), 0.0)
+            chunks.append(norms.mean(dim=(1, 2)).to(torch.float32))
+        col = torch.cat(chunks).contiguous() if chunks else torch.empty(0, dtype=torch.float32, device="cuda")
+        self.last_scores = self._all_scores(col, len(images))
+        return self._rank(col, lo, images, selection_count, descending=True)
 
     def get_unsure_samples(self, model, images, selection_count):
         # mean over valid pixels of 4 p1 - 4 p1^2 (accuracy.py:98-119)

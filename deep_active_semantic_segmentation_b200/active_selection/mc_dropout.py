@@ -46,6 +46,10 @@ class ActiveSelectionMCDropout(ActiveSelectionBase):
         N, H2, W2 = score_maps.shape
         dev_maps = score_maps if score_maps.is_cuda else score_maps.cuda()
         dev_maps = dev_maps.contiguous()
+        if dev_maps.data_ptr() == score_maps.data_ptr():
+            # the NMS kernel zeroes the windows of EVERY image-local pick; the reference's loop only those of the picks
+            # it actually takes (mc_dropout.py:97-103): work on a copy, replay the chosen windows on the caller's tensor
+            dev_maps = dev_maps.clone()
         kmax = max(1, min(math.ceil(max_selection_count), ops.nms_pick_bound(H2, W2, region_size)))
         regions, count = base.global_nms(dev_maps, 0, N, region_size, max_selection_count, kmax)
         # leave the caller's tensor in the state the reference leaves it in: chosen windows zeroed

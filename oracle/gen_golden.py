@@ -278,6 +278,50 @@ def gen_accuracy(name, seed, N, C, S, block, R, k, batch_size):
     print(f"[golden] {name}: labels={out['labels_scores'][:4]} softmax={out['softmax_scores'][:3]} regions={count}")
 
 
+def adv_unet(torch, C, seed):
+    """Tiny deterministic stand-in for `model.module.unet` (the accuracy predictor head): (C + 3) -> 8 -> 2 channels."""
+    torch.manual_seed(seed)
+    return torch.nn.Sequential(torch.nn.Conv2d(C + 3, 8, 3, padding=1), torch.nn.Tanh(), torch.nn.Conv2d(8, 2, 3, padding=1))
+
+
+def gen_accuracy_adv(name, seed, N, C, S, block, k, batch_size):
+    """ActiveSelectionAccuracy.get_adversarially_vulnarable_samples (accuracy.py:73-96): gradient norm of the error head
+    with respect to its input, through the reference class with a tiny convolutional `unet` (weights stored)."""
+    ref = ref_shim.load_reference()
+    torch = ref.torch
+    from active_selection import accuracy as ref_accuracy  # reference module
+
+    pool = make_pool(seed, N, 1, C, S, S, block)
+    paths = [str(i) for i in range(N)]
+    unet = adv_unet(torch, C, seed)
+
+    class AdvModel(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.unet = unet
+
+        @property
+        def module(self):
+            return self
+
+        def forward(self, x):
+            gs = [int(round(float(v) / ref_shim.GID_SCALE)) for v in x[:, 0, 0, 0]]
+            seg = torch.from_numpy(np.stack([pool.logits[g, 0] for g in gs]))
+            return seg, self.unet(torch.cat([torch.softmax(seg, dim=1), x], dim=1))
+
+    sel = ref.active_selection.get_active_selection_class("accuracy_labels", C, pool, S, batch_size)
+    cap = SortedCapture()
+    ref_accuracy.sorted = cap
+    chosen = sel.get_adversarially_vulnarable_samples(AdvModel(), paths, k)
+    del ref_accuracy.sorted
+    np.savez_compressed(
+        os.path.join(GOLDEN, name + ".npz"),
+        meta=np.array([seed, N, C, S, block, k, batch_size], dtype=np.int64), versions=versions(),
+        logits_sha=np.array(checksum(pool.logits)), scores=np.array(cap.calls[0][0], dtype=np.float32),
+        selected=paths_to_idx(chosen), **{"w_" + k_.replace(".", "_"): v.detach().numpy() for k_, v in unet.state_dict().items()})
+    print(f"[golden] {name}: scores={np.array(cap.calls[0][0])[:4]} selected={paths_to_idx(chosen)}")
+
+
 def gen_maxsubset():
     """ActiveSelectionMaxSubset._max_representative_samples (max_subset.py:17-39): the reference's own seeded
     fixture (tests.py:616-645, seed 27, 1000 x 1024 float64, 8 candidates, 4 picks) and two float32 pools with
@@ -307,6 +351,56 @@ def gen_maxsubset():
         out[f"{tag}_x_sha"], out[f"{tag}_y_sha"] = np.array(checksum(X)), np.array(checksum(Y))
     np.savez_compressed(os.path.join(GOLDEN, "maxsubset.npz"), versions=versions(), **out)
     print(f"[golden] maxsubset: reference fixture picks {ref_picks} of candidates {cand}; a={out['a_picks'][:6]} b={out['b_picks'][:6]}")
+
+
+def gen_maxsubset_poolers(name, seed, N, F_, fh, fw, crop, region_size, batch_size):
+    """The three feature poolers of ActiveSelectionMaxSubset (max_subset.py:49-70, 72-86, 88-111) and
+    get_representative_regions / get_representative_images on top of them, through the REFERENCE class.
+
+    The reference pools a region crop with `F.avg_pool2d(crop, (feature_h, feature_w))` - a kernel LARGER than the crop.
+    The torch the reference was written for (0.4 / 1.0) clipped such a window to the input and returned the crop mean;
+    torch 2.x refuses the call.  The generator therefore runs the reference's own loops (cell enumeration, floor
+    arithmetic, ordering, flattening) with ONE substitution in the reference module's namespace: an avg_pool2d whose
+    kernel is clipped to the input size - the old semantics, nothing else changed."""
+    ref = ref_shim.load_reference()
+    torch = ref.torch
+    import types
+    from active_selection import max_subset as ref_ms
+    real = torch.nn.functional
+
+    def clipped_avg_pool2d(x, kernel_size, stride=None, *a, **kw):
+        k = (kernel_size, kernel_size) if isinstance(kernel_size, int) else tuple(kernel_size)
+        k = (min(k[0], x.shape[-2]), min(k[1], x.shape[-1]))
+        return real.avg_pool2d(x, k, stride, *a, **kw)
+
+    ref_ms.F = types.SimpleNamespace(avg_pool2d=clipped_avg_pool2d)
+    rng = np.random.Generator(np.random.Philox(key=[seed, 78]))
+    feats = rng.standard_normal(size=(N, F_, fh, fw), dtype=np.float32)
+    feats += (rng.integers(0, 3, size=(N, 1, 1, 1)) * 0.75).astype(np.float32)
+    pool = ref_shim.SyntheticPool(np.zeros((N, 1, 2, crop, crop), np.float32), None, feats)
+    sel = ref.active_selection.get_max_subset_active_selector(pool, crop, batch_size)
+    paths = [str(i) for i in range(N)]
+    model = lambda: ref_shim.make_replay_model(pool, "deeplab")
+    cell_feats = np.stack(sel._get_features_for_image_regions(model(), paths, region_size)).astype(np.float32)
+    # candidate regions: (r, c, h, w) in image coordinates, two per candidate image, one touching the border
+    cand = {}
+    for i in range(0, N, 2):
+        cand[str(i)] = [(int(rng.integers(0, crop - region_size)), int(rng.integers(0, crop - region_size)), region_size, region_size),
+                        (crop - region_size, 0, region_size, region_size)]
+    li, lr = sel._convert_regions_to_list(cand)
+    region_feats = np.stack(sel._get_features_for_regions(model(), li, lr)).astype(np.float32)
+    selected_regions, n_sel = sel.get_representative_regions(model(), paths, cand, region_size)
+    out = dict(cell_features=cell_feats, region_features=region_feats, n_selected=np.int64(n_sel),
+               cand_rows=np.array([(int(k), *r) for k in sorted(cand) for r in cand[k]], dtype=np.int64),
+               selected_rows=np.array([(int(k), *r) for k in selected_regions for r in selected_regions[k]], dtype=np.int64))
+    if fh >= 64 and fw >= 64:       # the image-level pooler needs a 64 x 64 window (max_subset.py:79)
+        out["image_features"] = np.stack(sel._get_features_for_images(model(), paths)).astype(np.float32)
+        out["representative_images"] = paths_to_idx(sel.get_representative_images(model(), paths, paths[1::2]))
+    np.savez_compressed(os.path.join(GOLDEN, name + ".npz"),
+                        meta=np.array([seed, N, F_, fh, fw, crop, region_size, batch_size], dtype=np.int64),
+                        versions=versions(), features_sha=np.array(checksum(feats)), **out)
+    ref_ms.F = real
+    print(f"[golden] {name}: cells {cell_feats.shape}, regions {region_feats.shape}, selected {n_sel}")
 
 
 def gen_noise(name, seed, N, T, C, S, block, R, k, batch_size):
@@ -554,6 +648,11 @@ FIXTURES = {
     # ... and 33 -> 129 (3 x 3 tiles with ragged edges, 9 tiles deep windows)
     "upsample_mid": lambda: gen_upsample("upsample_mid", synth.DEFAULT_SEED + 11, N=3, T=3, C=19, h=33, w=33, H=129, W=129, block=4, k=1, batch_size=2),
     "accuracy_small": lambda: gen_accuracy("accuracy_small", 41, 6, 5, 40, 8, 9, 4, 3),
+    # max-subset feature poolers: 129 x 129 feature map of a 513 crop (DeepLab geometry, 128-pixel regions -> 32 x 32 cells)
+    "maxsubset_poolers": lambda: gen_maxsubset_poolers("maxsubset_poolers", 51, N=6, F_=12, fh=129, fw=129, crop=513, region_size=128, batch_size=4),
+    # ... and a rectangular feature map that the crop size does not divide (floor arithmetic of max_subset.py:59-62,100-107)
+    "maxsubset_poolers_rect": lambda: gen_maxsubset_poolers("maxsubset_poolers_rect", 52, N=5, F_=7, fh=33, fw=45, crop=130, region_size=40, batch_size=2),
+    "accuracy_adv": lambda: gen_accuracy_adv("accuracy_adv", 43, 5, 5, 24, 8, 3, 2),
     # BASELINE sizes (VERDICT r1 "next" 1a): config 2's plane through the reference, config 3's rectangular maps through
     # the restatement, config 5's N = 10 000 through the reference's sklearn loop
     "mc_baseline": lambda: gen_mc_baseline("mc_baseline", synth.DEFAULT_SEED + 20, N=2, T=20, C=19, H=512, W=1024, block=32, batch_size=2),

@@ -445,3 +445,70 @@ def test_mc_noise_input_perturbation_is_observed():
         o = R.mc_maps(logits[b], labels[b].cpu().numpy(), C)
         np.testing.assert_allclose(maps[b].cpu().numpy(), o["vote_entropy"], rtol=RTOL, atol=ATOL_MAP)
     assert float(torch.stack(maps).max()) > 0                          # the noise does flip votes on this model
+
+
+def test_handle_options_and_info():
+    """das_handle: per-device, options readable / writable, L2 geometry and SM count come from the device."""
+    import ctypes
+    from deep_active_semantic_segmentation_b200 import _lib
+    lib = _lib.load()
+    h = _lib.handle(0)
+    assert _lib.handle(0).value == h.value == _lib.handle(torch.device("cuda", 0)).value          # one handle per device
+    assert lib.das_handle_device(h) == 0
+    assert lib.das_handle_sm_count(h) == torch.cuda.get_device_properties(0).multi_processor_count
+    info = _lib.l2_info(0)
+    assert info["l2_bytes"] == torch.cuda.get_device_properties(0).L2_cache_size and info["persisting_max_bytes"] <= info["l2_bytes"]
+    old = _lib.set_option("mc_tma_ctas", 2)
+    assert _lib.get_option("mc_tma_ctas") == 2 and _lib.set_option("mc_tma_ctas", old) == 2
+    assert lib.das_handle_set_option(h, _lib.OPTIONS["mc_up_warps"], 7) == -1                       # only 0 / 4 / 15
+    assert lib.das_handle_set_option(h, 99, 1) == -1
+    v = ctypes.c_int()
+    assert lib.das_handle_get_option(h, _lib.OPTIONS["mc_tma"], ctypes.byref(v)) == 0 and v.value in (0, 1)
+    # a second, independent handle on the same device keeps its own options; destroying it leaves the first intact
+    h2 = ctypes.c_void_p()
+    assert lib.das_handle_create(0, ctypes.byref(h2)) == 0 and h2.value != h.value
+    assert lib.das_handle_set_option(h2, _lib.OPTIONS["mc_tma"], 0) == 0 and _lib.get_option("mc_tma") == 1
+    assert lib.das_handle_destroy(h2) == 0
+    assert lib.das_handle_create(torch.cuda.device_count() + 3, ctypes.byref(h2)) == -1
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs in one process")
+def test_two_devices_in_one_process():
+    """One handle per device: tensors on cuda:1 are scored while cuda:0 is the current device (the entry points switch
+    to the handle's device for the call), with the TMA path (per-handle descriptor cache) and k-center (per-handle
+    scratch), and both devices give the oracle's results."""
+    ops = _ops()
+    from deep_active_semantic_segmentation_b200 import _lib
+    B, T, C, H, W = 2, 5, 19, 32, 64
+    logits = synth.pool_logits(31, [0, 1], T, C, H, W, 8)
+    labels = synth.pool_labels(31, [0, 1], H, W, C, 8)
+    torch.cuda.set_device(0)
+    assert _lib.handle(0).value != _lib.handle(1).value
+    outs = []
+    for d in (1, 0, 1):
+        dev = torch.device("cuda", d)
+        ps = [torch.from_numpy(np.ascontiguousarray(logits[:, t])).to(dev) for t in range(T)]
+        st = ops.MCState(B, C, H, W, T, device=dev, single_shot=True)
+        out = st.score(ps, torch.from_numpy(labels).to(dev), maps=ops.MAP_NAMES, scores=True)
+        assert out["scores"].device == dev and torch.cuda.current_device() == 0
+        outs.append({k: v.cpu().numpy() for k, v in out.items()})
+        st2 = ops.MCState(B, C, H, W, T, device=dev)            # streaming form on the same device
+        for p in ps:
+            st2.accumulate(p)
+        fin = st2.finalize(torch.from_numpy(labels).to(dev), maps=("pred_entropy",))
+        np.testing.assert_array_equal(fin["pred_entropy"].cpu().numpy(), outs[-1]["pred_entropy"])
+    for k in outs[0]:
+        np.testing.assert_array_equal(outs[0][k], outs[1][k])
+        np.testing.assert_array_equal(outs[0][k], outs[2][k])
+    check_against_oracle(outs[0], logits, labels)
+    feats = synth.coreset_features(2, 600, 64)
+    want, _ = R.kcenter_greedy(feats, [0, 1, 2], 12)
+    for d in (1, 0):
+        f = torch.from_numpy(feats).to(f"cuda:{d}")
+        cen = torch.tensor([0, 1, 2], dtype=torch.int32, device=f.device)
+        md2 = torch.empty(600, dtype=torch.float64, device=f.device)
+        key = torch.zeros(2, dtype=torch.int64, device=f.device)
+        ops.kcenter_init(f, 0, 600, cen, md2, key)               # step-wise entry points: per-handle scratch table
+        assert int(key[1].item()) == want[0]
+        picks, _ = ops.kcenter_greedy(f, [0, 1, 2], 12)
+        assert picks.cpu().tolist() == want

@@ -364,3 +364,89 @@ def test_region_selector_on_low_resolution_logits_equals_full_resolution():
         sel = _factory("variance", C, pool, H, bs)
         out.append(sel.create_region_maps(fakes.ReplayModel(pool), _paths(N), existing, R, 2))
     assert out[0] == out[1] and out[0][1] > 0
+
+
+@pytest.mark.parametrize("name", ["maxsubset_poolers", "maxsubset_poolers_rect"])
+def test_maxsubset_feature_poolers_match_reference(name):
+    """max_subset.py:49-70, 72-86, 88-111 + get_representative_regions / _images: goldens from the reference class (its
+    own loops; only the avg_pool2d call that torch 2.x rejects runs with the kernel clipped to the crop - see
+    oracle/gen_golden.py:gen_maxsubset_poolers)."""
+    from deep_active_semantic_segmentation_b200.active_selection import get_max_subset_active_selector
+    g = G.load(name)
+    seed, N, F_, fh, fw, crop, region_size, bs = (int(v) for v in g["meta"])
+    rng = np.random.Generator(np.random.Philox(key=[seed, 78]))
+    feats = rng.standard_normal(size=(N, F_, fh, fw), dtype=np.float32)
+    feats += (rng.integers(0, 3, size=(N, 1, 1, 1)) * 0.75).astype(np.float32)
+    assert G.sha(feats) == str(g["features_sha"])
+    pool = fakes.Pool(np.zeros((N, 1, 2, crop, crop), np.float32), None, feats)
+    sel = get_max_subset_active_selector(pool, crop, bs)
+    paths = _paths(N)
+    model = lambda: fakes.ReplayModel(pool, "deeplab")
+    cells = sel._get_features_for_image_regions(model(), paths, region_size)
+    np.testing.assert_allclose(cells.cpu().numpy(), g["cell_features"], rtol=1e-5, atol=1e-6)
+    cand = {}
+    for row in g["cand_rows"].tolist():
+        cand.setdefault(str(row[0]), []).append(tuple(row[1:]))
+    li, lr = sel._convert_regions_to_list(cand)
+    regs = sel._get_features_for_regions(model(), li, lr)
+    np.testing.assert_allclose(regs.cpu().numpy(), g["region_features"], rtol=1e-5, atol=1e-6)
+    selected, n_sel = sel.get_representative_regions(model(), paths, cand, region_size)
+    assert n_sel == int(g["n_selected"])
+    assert sorted((int(k), *r) for k, lst in selected.items() for r in lst) == sorted(tuple(r) for r in g["selected_rows"].tolist())
+    if "image_features" in g.files:
+        imf = sel._get_features_for_images(model(), paths)
+        np.testing.assert_allclose(imf.cpu().numpy(), g["image_features"], rtol=1e-5, atol=1e-6)
+        rep = sel.get_representative_images(model(), paths, paths[1::2])
+        assert _idx(rep) == g["representative_images"].tolist()
+
+
+def test_adversarially_vulnerable_samples_match_reference():
+    """accuracy.py:73-96: gradient norm of the error head with respect to its input (network forward + backward in
+    PyTorch on the device, TF32 off), masking + image mean + ranking on the scoring path."""
+    g = G.load("accuracy_adv")
+    seed, N, C, S, block, k, bs = (int(v) for v in g["meta"])
+    logits, labels = G.pool_from_meta(seed, N, 1, C, S, S, block, g["logits_sha"])
+    pool = fakes.Pool(logits, labels)
+    unet = torch.nn.Sequential(torch.nn.Conv2d(C + 3, 8, 3, padding=1), torch.nn.Tanh(), torch.nn.Conv2d(8, 2, 3, padding=1))
+    unet.load_state_dict({k_[2:].replace("_", ".", 1): torch.from_numpy(g[k_]) for k_ in g.files if k_.startswith("w_")})
+    unet = unet.cuda()
+
+    class AdvModel(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.unet = unet
+
+        @property
+        def module(self):
+            return self
+
+        def forward(self, x):
+            gs = [int(round(float(v) / fakes.GID_SCALE)) for v in x[:, 0, 0, 0].cpu()]
+            seg = torch.from_numpy(np.stack([logits[i, 0] for i in gs])).cuda()
+            return seg, self.unet(torch.cat([torch.softmax(seg, dim=1), x], dim=1))
+
+    old = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        sel = _factory("accuracy_labels", C, pool, S, bs)
+        chosen = sel.get_adversarially_vulnarable_samples(AdvModel(), _paths(N), k)
+    finally:
+        torch.backends.cudnn.allow_tf32 = old
+    assert _idx(chosen) == g["selected"].tolist()
+    np.testing.assert_allclose(sel.last_scores, g["scores"], rtol=2e-5, atol=1e-7)
+
+
+def test_square_nms_leaves_the_callers_cuda_tensor_like_the_reference():
+    """mc_dropout.py:97-103 zeroes the windows of the picks it TAKES, nothing else - also when the caller hands in a
+    contiguous CUDA tensor (the NMS kernel itself zeroes the windows of every image-local pick)."""
+    from deep_active_semantic_segmentation_b200.active_selection import ActiveSelectionMCDropout
+    from oracle import restate as R
+    rng = np.random.default_rng(8)
+    m = rng.random((4, 20, 24)).astype(np.float32)
+    want_maps = m.copy()
+    want_sel, want_count = R.square_nms(want_maps, 5, 6.2)        # 7 picks: fewer than the image-local sequences hold
+    for dev in ("cuda", "cpu"):
+        t = torch.from_numpy(m.copy()).to(dev)
+        got_sel, got_count = ActiveSelectionMCDropout.square_nms(t, 5, 6.2)
+        assert (got_sel, got_count) == (want_sel, want_count)
+        np.testing.assert_array_equal(t.cpu().numpy(), want_maps)

@@ -258,3 +258,43 @@ def test_batch_feeder_falls_back_to_the_dataloader_without_cuda(monkeypatch):
     assert [b["image"].shape[0] for b in batches] == [2, 2, 1] and len(DeviceBatchLoader(DS(), 2, device="cpu")) == 3
     assert float(batches[2]["label"][0, 0, 0]) == -4.0 and not batches[0]["image"].is_cuda
     assert list(DeviceBatchLoader(torch.utils.data.TensorDataset(torch.zeros(0, 1)), 2, device="cpu")) == []
+
+
+def test_selections_txt_is_what_the_reference_tools_read_and_write(tmp_path):
+    """utils/saver.py:68-78 format, diffed by the reference's own utils/compare_selections.py when the reference tree
+    is present (this container), and by the in-package twin everywhere."""
+    from deep_active_semantic_segmentation_b200 import selections
+    from oracle import restate as R
+    from tests import golden_util as G
+
+    g = G.load("mc_small")
+    k = int(g["meta"][7])
+    ref_paths = [str(i).encode() for i in g["ve_selected"].tolist()]                      # what the reference selected
+    own_paths = [str(i).encode() for i in R.rank_topk(g["ve_scores"].tolist(), k, True)]  # restated ranking of its scores
+    r = G.load("region_small")
+    ref_regions = {}
+    for i, rr, cc, hh, ww in r["regions"].tolist():
+        ref_regions.setdefault(str(i).encode(), []).append((rr, cc, hh, ww))
+    a, b = str(tmp_path / "a"), str(tmp_path / "b")
+    for folder, paths in ((a, ref_paths), (b, own_paths)):
+        f0 = selections.write_selections(folder, paths, run=0)
+        selections.write_selections(folder, list(ref_regions), ref_regions, run=1)
+        assert open(f0).read() == "".join(p.decode() + "\n" for p in paths)
+    line = open(os.path.join(a, "run_0001", "selections.txt")).readline().strip().split(",")
+    first = next(iter(ref_regions))
+    assert line[0] == first.decode() and [int(v) for v in line[1:5]] == list(ref_regions[first][0])
+    assert (len(line) - 1) % 4 == 0
+    assert selections.compare_selections(a, b) == [("run_0000", k, k), ("run_0001", len(ref_regions), len(ref_regions))]
+    # the saver of the reference writes byte-identical files
+    ref_root = "/root/reference"
+    if os.path.isdir(ref_root):
+        out = subprocess.run([sys.executable, os.path.join(ref_root, "utils", "compare_selections.py"), a, b],
+                             capture_output=True, text=True)
+        assert out.returncode == 0, out.stderr
+        assert f"run_0000 = {k}/{k} (100.0)" in out.stdout and "run_0001" in out.stdout
+    # a diverging selection is reported, an unequal count is an error
+    selections.write_selections(b, own_paths[:-1] + [b"999"], run=0)
+    assert selections.compare_selections(a, b)[0] == ("run_0000", k - 1, k)
+    selections.write_selections(b, own_paths[:-1], run=0)
+    with pytest.raises(ValueError):
+        selections.compare_selections(a, b)
