@@ -476,7 +476,7 @@ def config_records(args, world, rank, dev, peaks):
 
             def __init__(self):
                 super().__init__()
-                self.gen = torch.Generator(device=dev).manual_seed(5)
+                self.gen = torch.Generator(device=dev).manual_seed(5 + 7919 * rank)     # distinct rows on every rank
                 self.buf = torch.empty((B, 304, 129, 129), device=dev)
 
             @property

@@ -60,6 +60,7 @@ _PROTOTYPES = {
     "das_mc_upsample_supported": (_i, [_h, _i, _i, _i, _i]),
     "das_mc_votes_ptr": (_i, [C.POINTER(McDesc), _vp, C.POINTER(_vp)]),
     "das_suppress_rects": (_i, [_h, _vp, _i, _i, _i, _vp, _i, _vp]),
+    "das_suppress_rects_host": (_i, [_h, _vp, _i, _i, _i, C.POINTER(C.c_int32), _i, _vp]),
     "das_add_maps": (_i, [_h, _vp, _vp, _sz, _vp]),
     "das_box_sum_workspace_bytes": (_i, [_i, _i, _i, _i, C.POINTER(_sz)]),
     "das_minmax_init": (_i, [_h, _vp, _vp]),

@@ -31,30 +31,55 @@ __device__ __forceinline__ bool kc_better(double v, int i, double bv, int bi) {
     return v > bv || (v == bv && i < bi);  // larger distance, then lower row index
 }
 
-// squared distance between rows a and b (length D) by one warp, fp64 accumulation
+// squared distance between rows a and b (length D) by one warp, fp64 accumulation.
+// Four independent partial sums per lane (iteration parity x two halves of a float4): the exact re-evaluation of a row
+// sits on the critical path of every greedy step, and the chains of dependent DFMAs per lane were a large part of it
+// (eight chains spill in the 64-register cluster kernel).  The association (c0 + c1) -> warp xor-tree is the definition
+// of the value: every path (init, step, chain, cluster, filtered or not) calls this one function, so min_d2 stays
+// bit-identical between them.
 template <bool VEC4>
 __device__ __forceinline__ double warp_dist2(const float* __restrict__ a, const float* __restrict__ b, int D, int lane) {
-    double s0 = 0.0, s1 = 0.0;
     if (VEC4) {
         const float4* a4 = reinterpret_cast<const float4*>(a);
         const float4* b4 = reinterpret_cast<const float4*>(b);
-#pragma unroll 8  // 16 independent 128-bit loads in flight per lane: the loop is L2-latency bound otherwise
-        for (int i = lane; i < D / 4; i += 32) {
+        double s[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+        const int n4 = D / 4;
+        int i = lane;
+#pragma unroll 4  // 4 x 2 x 2 = 16 independent 128-bit loads in flight per lane (L2 latency)
+        for (; i + 32 < n4; i += 64) {
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                const float4 x = a4[i + 32 * q], y = b4[i + 32 * q];
+                const double d0 = (double)x.x - (double)y.x, d1 = (double)x.y - (double)y.y;
+                const double d2 = (double)x.z - (double)y.z, d3 = (double)x.w - (double)y.w;
+                s[q][0] = fma(d0, d0, s[q][0]);
+                s[q][1] = fma(d1, d1, s[q][1]);
+                s[q][0] = fma(d2, d2, s[q][0]);
+                s[q][1] = fma(d3, d3, s[q][1]);
+            }
+        }
+        if (i < n4) {  // ragged tail: one more iteration of the even chain
             const float4 x = a4[i], y = b4[i];
             const double d0 = (double)x.x - (double)y.x, d1 = (double)x.y - (double)y.y;
             const double d2 = (double)x.z - (double)y.z, d3 = (double)x.w - (double)y.w;
-            s0 = fma(d0, d0, s0);
-            s1 = fma(d1, d1, s1);
-            s0 = fma(d2, d2, s0);
-            s1 = fma(d3, d3, s1);
+            s[0][0] = fma(d0, d0, s[0][0]);
+            s[0][1] = fma(d1, d1, s[0][1]);
+            s[0][0] = fma(d2, d2, s[0][0]);
+            s[0][1] = fma(d3, d3, s[0][1]);
         }
-    } else {
-        for (int i = lane; i < D; i += 32) {
-            const double d = (double)a[i] - (double)b[i];
-            s0 = fma(d, d, s0);
-        }
+        return warp_sum((s[0][0] + s[0][1]) + (s[1][0] + s[1][1]));
     }
-    return warp_sum(s0 + s1);
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+    int i = lane;
+    for (; i + 96 < D; i += 128) {
+        const double d0 = (double)a[i] - (double)b[i], d1 = (double)a[i + 32] - (double)b[i + 32];
+        const double d2 = (double)a[i + 64] - (double)b[i + 64], d3 = (double)a[i + 96] - (double)b[i + 96];
+        s0 = fma(d0, d0, s0), s1 = fma(d1, d1, s1), s2 = fma(d2, d2, s2), s3 = fma(d3, d3, s3);
+    }
+    if (i < D) { const double d = (double)a[i] - (double)b[i]; s0 = fma(d, d, s0); }
+    if (i + 32 < D) { const double d = (double)a[i + 32] - (double)b[i + 32]; s1 = fma(d, d, s1); }
+    if (i + 64 < D) { const double d = (double)a[i + 64] - (double)b[i + 64]; s2 = fma(d, d, s2); }
+    return warp_sum((s0 + s1) + (s2 + s3));
 }
 
 // MODE 0: init  - min over the L given centres              (core_set.py:19)

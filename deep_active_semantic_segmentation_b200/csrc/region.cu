@@ -21,6 +21,23 @@ __global__ void suppress_rects_kernel(float* maps, int B, int H, int W, const in
     for (int i = threadIdx.x; i < cells; i += blockDim.x) m[(size_t)(r0 + i / w) * W + c0 + i % w] = 0.f;
 }
 
+// the same with the records passed BY VALUE in the kernel parameters (host rects: no host-to-device copy, which for a
+// pageable source would be a synchronous one and stall the batch pipeline of create_region_maps)
+constexpr int kRectsPerLaunch = 128;
+struct RectBlock {
+    int32_t v[kRectsPerLaunch * 5];
+};
+__global__ void suppress_rects_param_kernel(float* maps, int B, int H, int W, const __grid_constant__ RectBlock rb) {
+    const int32_t* q = rb.v + blockIdx.x * 5;
+    const int img = q[0];
+    if (img < 0 || img >= B) return;
+    const int r0 = min(max(q[1], 0), H), c0 = min(max(q[2], 0), W);
+    const int r1 = min(max(q[1] + q[3], r0), H), c1 = min(max(q[2] + q[4], c0), W);
+    const int w = c1 - c0, cells = (r1 - r0) * w;
+    float* m = maps + (size_t)img * H * W;
+    for (int i = threadIdx.x; i < cells; i += blockDim.x) m[(size_t)(r0 + i / w) * W + c0 + i % w] = 0.f;
+}
+
 __global__ void add_maps_kernel(float* a, const float* b, size_t n) {
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
         a[i] = a[i] + b[i];
@@ -215,6 +232,19 @@ int das_suppress_rects(das_handle* h, float* maps, int B, int H, int W, const in
     if (n == 0) return DAS_OK;
     DAS_LAUNCH(suppress_rects_kernel, n, 256, 0, (cudaStream_t)stream, maps, B, H, W, rects, n);
     DAS_CHECK_LAUNCH();
+    return DAS_OK;
+}
+
+int das_suppress_rects_host(das_handle* h, float* maps, int B, int H, int W, const int32_t* host_rects, int n, void* stream) {
+    DAS_ENTER(h);
+    if (maps == nullptr || B <= 0 || H <= 0 || W <= 0 || n < 0 || (n > 0 && host_rects == nullptr)) return DAS_ERR_INVALID_ARG;
+    for (int i0 = 0; i0 < n; i0 += kRectsPerLaunch) {
+        const int m = n - i0 < kRectsPerLaunch ? n - i0 : kRectsPerLaunch;
+        RectBlock rb;
+        for (int j = 0; j < m * 5; ++j) rb.v[j] = host_rects[(size_t)i0 * 5 + j];
+        DAS_LAUNCH(suppress_rects_param_kernel, m, 256, 0, (cudaStream_t)stream, maps, B, H, W, rb);
+        DAS_CHECK_LAUNCH();
+    }
     return DAS_OK;
 }
 

@@ -215,10 +215,19 @@ def suppress_rects(maps: torch.Tensor, rects) -> None:
         raise DasError("maps must be contiguous (modified in place)")
     if len(rects) == 0:
         return
-    r = torch.as_tensor(rects, dtype=torch.int32).reshape(-1, 5).to(maps.device)
     B, H, W = maps.shape
-    check(_lib.load().das_suppress_rects(_h(maps.device), _ptr(maps), B, H, W, _ptr(r), r.shape[0], _stream(maps.device)),
-          "das_suppress_rects")
+    if isinstance(rects, torch.Tensor) and rects.is_cuda:
+        r = rects.to(torch.int32).reshape(-1, 5).contiguous()
+        check(_lib.load().das_suppress_rects(_h(maps.device), _ptr(maps), B, H, W, _ptr(r), r.shape[0],
+                                             _stream(maps.device)), "das_suppress_rects")
+        return
+    # host records (the caller's lists): passed in the kernel parameters - no upload, no synchronisation
+    flat = [int(v) for rec in (rects.tolist() if isinstance(rects, torch.Tensor) else rects) for v in rec]
+    if len(flat) % 5:
+        raise DasError("suppress_rects: records are (image, r, c, h, w)")
+    arr = (C.c_int32 * len(flat))(*flat)
+    check(_lib.load().das_suppress_rects_host(_h(maps.device), _ptr(maps), B, H, W, arr, len(flat) // 5,
+                                              _stream(maps.device)), "das_suppress_rects_host")
 
 
 def add_maps(a: torch.Tensor, b: torch.Tensor) -> None:

@@ -198,6 +198,10 @@ int das_mc_votes_ptr(const das_mc_desc* desc, void* state, uint8_t** votes);
 /* ActiveSelectionMCDropout.suppress_labeled_entropy (mc_dropout.py:110-121):
  * zero maps[i, r:r+h, c:c+w] for each of the n records (i, r, c, h, w) in `rects` (device, int32). */
 int das_suppress_rects(das_handle* h, float* maps, int B, int H, int W, const int32_t* rects, int n, void* stream);
+/* The same with the records in HOST memory (the caller's Python list of labelled regions, region_cityscapes.py:54-61):
+ * they travel in the kernel parameters, 128 per launch - no host-to-device copy, nothing to keep alive after the call. */
+int das_suppress_rects_host(das_handle* h, float* maps, int B, int H, int W, const int32_t* host_rects, int n,
+                            void* stream);
 
 /* a += b elementwise (combined noise + dropout vote entropy, mc_noise.py:141,165) */
 int das_add_maps(das_handle* h, float* a, const float* b, size_t n, void* stream);
