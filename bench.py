@@ -35,6 +35,7 @@ if ROOT not in sys.path:
 
 H, W, C, T = 512, 1024, 19, 20
 POOL_IMAGES, TOPK = 2975, 125
+NUMA_INFO = None
 METRIC = "pool images scored/sec (T MC passes, entropy+BALD+top-k)"
 UNIT = "images/s"
 WORKLOAD = "mc_dropout_entropy_bald_cityscapes_pool_512x1024_c19_t20"
@@ -134,6 +135,11 @@ def init_dist(n_gpus: int):
     if world > 1:
         import torch.distributed as td
         torch.cuda.set_device(local)
+        if os.environ.get("DAS_NUMA_BIND", "1") != "0":
+            # every rank next to its GPU: pinned host buffers are then allocated on the GPU's NUMA node
+            from deep_active_semantic_segmentation_b200 import dist as _dist
+            global NUMA_INFO
+            NUMA_INFO = _dist.bind_to_gpu_numa_node(local)
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         # NCCL writes its version banner to stdout when the first communicator is created; stdout must carry
         # exactly one JSON line, so the banner is sent to stderr (fd level: it comes from C code)

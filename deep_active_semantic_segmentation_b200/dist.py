@@ -31,6 +31,39 @@ def _comm_device():
     return torch.device("cpu")
 
 
+def bind_to_gpu_numa_node(device_index: int) -> dict:
+    """Pin the calling process to the CPU cores of the NUMA node its GPU hangs off (sysfs: the PCI device's numa_node
+    and that node's cpulist), so that the pinned staging buffers it allocates afterwards are first-touched on that node
+    and its copy threads run next to them.  torchrun starts one process per GPU without any binding: on a two-socket
+    box half of the ranks then feed their GPU across the socket interconnect.  Returns what was done (for logs);
+    does nothing when the topology is not visible (containers without sysfs, single-node machines)."""
+    import os
+
+    info = {"device": int(device_index), "bound": False}
+    try:
+        bus = torch.cuda.get_device_properties(device_index).pci_bus_id
+        dom = getattr(torch.cuda.get_device_properties(device_index), "pci_domain_id", 0)
+        dev = getattr(torch.cuda.get_device_properties(device_index), "pci_device_id", 0)
+        sysdev = "/sys/bus/pci/devices/%04x:%02x:%02x.0" % (dom, bus, dev)
+        with open(os.path.join(sysdev, "numa_node")) as f:
+            node = int(f.read().strip())
+        info["numa_node"] = node
+        if node < 0:
+            return info
+        with open("/sys/devices/system/node/node%d/cpulist" % node) as f:
+            cpus = set()
+            for part in f.read().strip().split(","):
+                lo, _, hi = part.partition("-")
+                cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = os.sched_getaffinity(0) & cpus
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+            info.update(bound=True, cpus=len(allowed))
+    except Exception as exc:  # topology not visible: run unbound, as before
+        info["error"] = repr(exc)[:120]
+    return info
+
+
 def shard_bounds(n: int, world_size: int, rank: int):
     per = -(-n // world_size) if n > 0 else 0
     lo = min(n, rank * per)

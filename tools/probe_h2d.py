@@ -48,8 +48,14 @@ def main():
         cpus = len(os.sched_getaffinity(0))
     except AttributeError:
         cpus = os.cpu_count()
+    if world > 1:
+        import torch.distributed as td
+        numa = [None] * world
+        td.all_gather_object(numa, bench.NUMA_INFO)
+    else:
+        numa = [bench.NUMA_INFO]
     if rank == 0:
-        print(json.dumps({"n_gpus": world, "host_cores_visible": cpus, "bytes_per_copy": n, **out}), flush=True)
+        print(json.dumps({"n_gpus": world, "host_cores_visible": cpus, "bytes_per_copy": n, "numa": numa, **out}), flush=True)
     if world > 1:
         import torch.distributed as td
         td.destroy_process_group()
