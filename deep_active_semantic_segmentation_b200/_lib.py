@@ -9,7 +9,8 @@ import ctypes as C
 import os
 
 PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(PKG, "libdas_b200.so")
+# DAS_B200_LIB: load another build of the library (A/B measurements of kernel variants); default = the in-tree build
+LIB_PATH = os.environ.get("DAS_B200_LIB") or os.path.join(PKG, "libdas_b200.so")
 
 ABI_VERSION = 4
 MC_VOTES = 1

@@ -31,24 +31,56 @@ __device__ __forceinline__ bool kc_better(double v, int i, double bv, int bi) {
     return v > bv || (v == bv && i < bi);  // larger distance, then lower row index
 }
 
-// squared distance between rows a and b (length D) by one warp, fp64 accumulation.
-// Four independent partial sums per lane (iteration parity x two halves of a float4): the exact re-evaluation of a row
-// sits on the critical path of every greedy step, and the chains of dependent DFMAs per lane were a large part of it
-// (eight chains spill in the 64-register cluster kernel).  The association (c0 + c1) -> warp xor-tree is the definition
-// of the value: every path (init, step, chain, cluster, filtered or not) calls this one function, so min_d2 stays
-// bit-identical between them.
+// Squared distance between rows a and b (length D), fp64 accumulation of exact float32 differences.
+// The VALUE is defined as (Q0 + Q1) + (Q2 + Q3), where quarter Q_q sums the elements of the loop iterations it with
+// it % 4 == q (a warp covers 32 float4 / floats per iteration) - per lane two chains (x,z | y,w components) added
+// once, then the warp xor-tree.  One warp can evaluate all four quarters (warp_dist2: init / step / chain kernels) or
+// four warps one quarter each (warp_dist2_quarter: the cluster kernel, where the exact re-evaluation of ~11 rows per
+// CTA sits on the critical path of every greedy step - measured 4.3 of its 8.7 us): same association, same bits.
 template <bool VEC4>
-__device__ __forceinline__ double warp_dist2(const float* __restrict__ a, const float* __restrict__ b, int D, int lane) {
+__device__ __forceinline__ double lane_quarter(const float* __restrict__ a, const float* __restrict__ b, int D, int lane, int q) {
     if (VEC4) {
         const float4* a4 = reinterpret_cast<const float4*>(a);
         const float4* b4 = reinterpret_cast<const float4*>(b);
-        double s[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+        double s0 = 0.0, s1 = 0.0;
+        const int n4 = D / 4;
+#pragma unroll 4
+        for (int i = lane + 32 * q; i < n4; i += 128) {
+            const float4 x = a4[i], y = b4[i];
+            const double d0 = (double)x.x - (double)y.x, d1 = (double)x.y - (double)y.y;
+            const double d2 = (double)x.z - (double)y.z, d3 = (double)x.w - (double)y.w;
+            s0 = fma(d0, d0, s0);
+            s1 = fma(d1, d1, s1);
+            s0 = fma(d2, d2, s0);
+            s1 = fma(d3, d3, s1);
+        }
+        return s0 + s1;
+    }
+    double s = 0.0;
+    for (int i = lane + 32 * q; i < D; i += 128) {
+        const double d = (double)a[i] - (double)b[i];
+        s = fma(d, d, s);
+    }
+    return s;
+}
+template <bool VEC4>
+__device__ __forceinline__ double warp_dist2_quarter(const float* __restrict__ a, const float* __restrict__ b, int D, int lane,
+                                                     int q) {
+    return warp_sum(lane_quarter<VEC4>(a, b, D, lane, q));
+}
+template <bool VEC4>
+__device__ __forceinline__ double warp_dist2(const float* __restrict__ a, const float* __restrict__ b, int D, int lane) {
+    if (VEC4) {
+        // all four quarters in one sweep (eight independent chains, 8 loads in flight per iteration)
+        const float4* a4 = reinterpret_cast<const float4*>(a);
+        const float4* b4 = reinterpret_cast<const float4*>(b);
+        double s[4][2] = {{0.0, 0.0}, {0.0, 0.0}, {0.0, 0.0}, {0.0, 0.0}};
         const int n4 = D / 4;
         int i = lane;
-#pragma unroll 4  // 4 x 2 x 2 = 16 independent 128-bit loads in flight per lane (L2 latency)
-        for (; i + 32 < n4; i += 64) {
+#pragma unroll 2
+        for (; i + 96 < n4; i += 128) {
 #pragma unroll
-            for (int q = 0; q < 2; ++q) {
+            for (int q = 0; q < 4; ++q) {
                 const float4 x = a4[i + 32 * q], y = b4[i + 32 * q];
                 const double d0 = (double)x.x - (double)y.x, d1 = (double)x.y - (double)y.y;
                 const double d2 = (double)x.z - (double)y.z, d3 = (double)x.w - (double)y.w;
@@ -58,28 +90,25 @@ __device__ __forceinline__ double warp_dist2(const float* __restrict__ a, const 
                 s[q][1] = fma(d3, d3, s[q][1]);
             }
         }
-        if (i < n4) {  // ragged tail: one more iteration of the even chain
-            const float4 x = a4[i], y = b4[i];
-            const double d0 = (double)x.x - (double)y.x, d1 = (double)x.y - (double)y.y;
-            const double d2 = (double)x.z - (double)y.z, d3 = (double)x.w - (double)y.w;
-            s[0][0] = fma(d0, d0, s[0][0]);
-            s[0][1] = fma(d1, d1, s[0][1]);
-            s[0][0] = fma(d2, d2, s[0][0]);
-            s[0][1] = fma(d3, d3, s[0][1]);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {  // ragged tail: every remaining iteration stays in its quarter
+            if (i + 32 * q < n4) {
+                const float4 x = a4[i + 32 * q], y = b4[i + 32 * q];
+                const double d0 = (double)x.x - (double)y.x, d1 = (double)x.y - (double)y.y;
+                const double d2 = (double)x.z - (double)y.z, d3 = (double)x.w - (double)y.w;
+                s[q][0] = fma(d0, d0, s[q][0]);
+                s[q][1] = fma(d1, d1, s[q][1]);
+                s[q][0] = fma(d2, d2, s[q][0]);
+                s[q][1] = fma(d3, d3, s[q][1]);
+            }
         }
-        return warp_sum((s[0][0] + s[0][1]) + (s[1][0] + s[1][1]));
+        const double q0 = warp_sum(s[0][0] + s[0][1]), q1 = warp_sum(s[1][0] + s[1][1]);
+        const double q2 = warp_sum(s[2][0] + s[2][1]), q3 = warp_sum(s[3][0] + s[3][1]);
+        return (q0 + q1) + (q2 + q3);
     }
-    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-    int i = lane;
-    for (; i + 96 < D; i += 128) {
-        const double d0 = (double)a[i] - (double)b[i], d1 = (double)a[i + 32] - (double)b[i + 32];
-        const double d2 = (double)a[i + 64] - (double)b[i + 64], d3 = (double)a[i + 96] - (double)b[i + 96];
-        s0 = fma(d0, d0, s0), s1 = fma(d1, d1, s1), s2 = fma(d2, d2, s2), s3 = fma(d3, d3, s3);
-    }
-    if (i < D) { const double d = (double)a[i] - (double)b[i]; s0 = fma(d, d, s0); }
-    if (i + 32 < D) { const double d = (double)a[i + 32] - (double)b[i + 32]; s1 = fma(d, d, s1); }
-    if (i + 64 < D) { const double d = (double)a[i + 64] - (double)b[i + 64]; s2 = fma(d, d, s2); }
-    return warp_sum((s0 + s1) + (s2 + s3));
+    const double q0 = warp_sum(lane_quarter<false>(a, b, D, lane, 0)), q1 = warp_sum(lane_quarter<false>(a, b, D, lane, 1));
+    const double q2 = warp_sum(lane_quarter<false>(a, b, D, lane, 2)), q3 = warp_sum(lane_quarter<false>(a, b, D, lane, 3));
+    return (q0 + q1) + (q2 + q3);
 }
 
 // MODE 0: init  - min over the L given centres              (core_set.py:19)
@@ -347,9 +376,15 @@ constexpr int kClThreads = 1024;
 constexpr int kClWarps = kClThreads / 32;
 constexpr int kClRows = 4;  // rows per thread -> N <= 8 * 1024 * 4 = 32768
 
-struct __align__(16) ClBest {  // 32 bytes: the (v, nrm) pair is published with one 16-byte remote store
-    double v, nrm;
-    int idx, pad[3];
+// What a CTA publishes per step, in every peer's shared memory: ONE 16-byte remote store {value, row, tag = step + 1}.
+// A 16-byte aligned vector store to shared memory is a single transaction, so a reader that sees the tag of the step
+// also sees the value and the row that came with it: the peers poll their own copy of the table instead of meeting at a
+// hardware cluster barrier (whose release half is a MEMBAR.ALL.GPU per step).  Two tables (step parity): a CTA can be
+// at most one step ahead of the slowest one, because its next record needs every peer's record of this step.
+struct __align__(16) ClBest {
+    double v;
+    int idx;
+    unsigned int tag;
 };
 
 __device__ __forceinline__ void cluster_barrier() {
@@ -361,10 +396,9 @@ template <bool VEC4>
 __global__ void __cluster_dims__(kClCtas, 1, 1) __launch_bounds__(kClThreads, 1)
     kcenter_cluster_kernel(const float* __restrict__ feats, int N, int D, double* __restrict__ min_d2, int K,
                            int32_t* __restrict__ picks, double* __restrict__ min_d_out, const KcFilter f, int stage_centre) {
-    extern __shared__ float4 cl_dyn[];  // [centre row][wl_val f64 x 4096][wl_row i32 x 4096]
+    extern __shared__ float4 cl_dyn[];  // [centre row][wl_val f64 x 4 quarters x 4096][wl_row i32 x 4096]
     __shared__ ClBest slots[2][kClCtas];
     __shared__ double sv[kClWarps];
-    __shared__ double sn[kClWarps];
     __shared__ int si[kClWarps];
     __shared__ int wl_n;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -372,8 +406,15 @@ __global__ void __cluster_dims__(kClCtas, 1, 1) __launch_bounds__(kClThreads, 1)
     asm("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
     const size_t row_f4 = stage_centre ? ((size_t)D * sizeof(float) + 15) / 16 : 0;
     float* centre_row = reinterpret_cast<float*>(cl_dyn);
-    double* wl_val = reinterpret_cast<double*>(cl_dyn + row_f4);
-    int* wl_row = reinterpret_cast<int*>(wl_val + kClThreads * kClRows);
+    double* wl_val = reinterpret_cast<double*>(cl_dyn + row_f4);           // [slot][quarter]
+    int* wl_row = reinterpret_cast<int*>(wl_val + 4 * kClThreads * kClRows);
+    if (tid == 0) wl_n = 0;
+    if (tid < 2 * kClCtas) {
+        ClBest z;
+        z.v = 0.0, z.idx = -1, z.tag = 0u;
+        (&slots[0][0])[tid] = z;
+    }
+    __syncthreads();
 
     // rows of this thread: g + j * 8192 (coalesced across the cluster for every j)
     const int g = (int)rank * kClThreads + tid;
@@ -390,47 +431,60 @@ __global__ void __cluster_dims__(kClCtas, 1, 1) __launch_bounds__(kClThreads, 1)
 
     for (int s = 0; s < K; ++s) {
         // ---- local arg-max of the current min_d2 ----
-        double bv = -1.0, bn = 0.0;
+        double bv = -1.0;
         int bi = -1;
 #pragma unroll
         for (int j = 0; j < kClRows; ++j) {
             const int row = g + j * kClCtas * kClThreads;
-            if (row < N && (bi < 0 || kc_better(m[j], row, bv, bi))) bv = m[j], bi = row, bn = nr[j];
+            if (row < N && (bi < 0 || kc_better(m[j], row, bv, bi))) bv = m[j], bi = row;
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
-            const double ov = __shfl_xor_sync(0xffffffffu, bv, o), on = __shfl_xor_sync(0xffffffffu, bn, o);
+            const double ov = __shfl_xor_sync(0xffffffffu, bv, o);
             const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-            if (oi >= 0 && (bi < 0 || kc_better(ov, oi, bv, bi))) bv = ov, bi = oi, bn = on;
+            if (oi >= 0 && (bi < 0 || kc_better(ov, oi, bv, bi))) bv = ov, bi = oi;
         }
-        if (lane == 0) sv[wid] = bv, si[wid] = bi, sn[wid] = bn;
+        if (lane == 0) sv[wid] = bv, si[wid] = bi;
         __syncthreads();
         if (wid == 0) {
-            bv = sv[lane], bi = si[lane], bn = sn[lane];
+            bv = sv[lane], bi = si[lane];
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) {
-                const double ov = __shfl_xor_sync(0xffffffffu, bv, o), on = __shfl_xor_sync(0xffffffffu, bn, o);
+                const double ov = __shfl_xor_sync(0xffffffffu, bv, o);
                 const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-                if (oi >= 0 && (bi < 0 || kc_better(ov, oi, bv, bi))) bv = ov, bi = oi, bn = on;
+                if (oi >= 0 && (bi < 0 || kc_better(ov, oi, bv, bi))) bv = ov, bi = oi;
             }
-            if (lane < kClCtas) {  // lane t publishes this CTA's best in CTA t's slot table
+            if (lane < kClCtas) {  // lane t publishes this CTA's best in CTA t's slot table: one 16-byte store
                 const uint32_t local = (uint32_t)__cvta_generic_to_shared(&slots[parity][rank]);
                 uint32_t remote;
                 asm("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local), "r"(lane));
-                asm volatile("st.shared::cluster.v2.f64 [%0], {%1, %2};" ::"r"(remote), "d"(bv), "d"(bn) : "memory");
-                asm volatile("st.shared::cluster.u32 [%0], %1;" ::"r"(remote + 16), "r"(bi) : "memory");
+                const unsigned long long vb = (unsigned long long)__double_as_longlong(bv);
+                asm volatile("st.shared::cluster.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(remote), "r"((uint32_t)vb),
+                             "r"((uint32_t)(vb >> 32)), "r"((uint32_t)bi), "r"((uint32_t)(s + 1))
+                             : "memory");
             }
         }
-        cluster_barrier();
-        // ---- every thread reduces the 8 published records: the next centre ----
-        double cv = -1.0, nc = 0.0;
+        // ---- every thread waits for the 8 records of this step and reduces them: the next centre ----
+        double cv = -1.0;
         int centre = -1;
+        {
+            const uint32_t base = (uint32_t)__cvta_generic_to_shared(&slots[parity][0]);
 #pragma unroll
-        for (int r = 0; r < kClCtas; ++r) {
-            const ClBest q = slots[parity][r];
-            if (q.idx >= 0 && (centre < 0 || kc_better(q.v, q.idx, cv, centre))) cv = q.v, centre = q.idx, nc = q.nrm;
+            for (int r = 0; r < kClCtas; ++r) {
+                uint32_t w0, w1, w2, w3;
+                do {
+                    asm volatile("ld.volatile.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
+                                 : "=r"(w0), "=r"(w1), "=r"(w2), "=r"(w3)
+                                 : "r"(base + 16u * r)
+                                 : "memory");
+                } while (w3 != (uint32_t)(s + 1));
+                const double qv = __longlong_as_double((long long)(((unsigned long long)w1 << 32) | w0));
+                const int qi = (int)w2;
+                if (qi >= 0 && (centre < 0 || kc_better(qv, qi, cv, centre))) cv = qv, centre = qi;
+            }
         }
         parity ^= 1;
+        const double nc = f.nrm[centre];  // L2 resident; overlaps the screening loads below
         if (rank == 0 && tid == 0) picks[s] = centre;
 
         // ---- screen own rows with the tensor-core distances, exact float64 for the rest ----
@@ -452,8 +506,8 @@ __global__ void __cluster_dims__(kClCtas, 1, 1) __launch_bounds__(kClThreads, 1)
             }
             fc = centre_row;
         }
-        if (tid == 0) wl_n = 0;
-        __syncthreads();
+        __syncthreads();  // (kept on purpose: without it - wl_n is already reset, the staged row is only read after the
+                          //  next barrier - the loop measured 10 % SLOWER, 3.34 vs 3.03 ms: the warps then drift apart)
         int slot[kClRows];
 #pragma unroll
         for (int j = 0; j < kClRows; ++j) {
@@ -474,15 +528,19 @@ __global__ void __cluster_dims__(kClCtas, 1, 1) __launch_bounds__(kClThreads, 1)
         }
         __syncthreads();
         const int n_work = wl_n;
-        for (int k = wid; k < n_work; k += kClWarps) {
-            const double d = warp_dist2<VEC4>(feats + (size_t)wl_row[k] * D, fc, D, lane);
-            if (lane == 0) wl_val[k] = d;
+        // four warps per work-list row, one quarter of the distance each (see warp_dist2): a quarter of the latency
+        for (int k4 = wid; k4 < 4 * n_work; k4 += kClWarps) {
+            const double d = warp_dist2_quarter<VEC4>(feats + (size_t)wl_row[k4 >> 2] * D, fc, D, lane, k4 & 3);
+            if (lane == 0) wl_val[k4] = d;
         }
-        if (tid == 0) n_exact += (unsigned long long)n_work;
         __syncthreads();
+        if (tid == 0) n_exact += (unsigned long long)n_work, wl_n = 0;  // every thread has read n_work; next use is after a barrier
 #pragma unroll
         for (int j = 0; j < kClRows; ++j)
-            if (slot[j] >= 0) m[j] = fmin(m[j], wl_val[slot[j]]);
+            if (slot[j] >= 0) {
+                const double* p4 = wl_val + 4 * slot[j];
+                m[j] = fmin(m[j], (p4[0] + p4[1]) + (p4[2] + p4[3]));
+            }
     }
 
 #pragma unroll
@@ -682,8 +740,8 @@ int das_kcenter_greedy(das_handle* h, const float* feats, int N, int D, const in
         if (N <= kClCtas * kClThreads * kClRows && h->opt[DAS_OPT_KC_CLUSTER]) {
             // the whole loop inside one thread-block cluster
             const size_t row_bytes = (size_t)D * sizeof(float);
-            const int stage_centre = row_bytes <= 96 * 1024 ? 1 : 0;
-            const size_t smem = (stage_centre ? align_up(row_bytes, 16) : 0) + (size_t)kClThreads * kClRows * (8 + 4);
+            const int stage_centre = row_bytes <= 64 * 1024 ? 1 : 0;  // + 144 KB of work-list tables <= 227 KB
+            const size_t smem = (stage_centre ? align_up(row_bytes, 16) : 0) + (size_t)kClThreads * kClRows * (4 * 8 + 4);
             if (v4) {
                 DAS_CUDA(cudaFuncSetAttribute(kcenter_cluster_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
                 DAS_LAUNCH((kcenter_cluster_kernel<true>), kClCtas, kClThreads, smem, st, feats, N, D, w.d2, K, picks, min_d, f,
