@@ -727,7 +727,10 @@ def fused_upsample_variant(args, dev, steps=60):
     px = B * H * W
     mufu_ops = px * (T * (C + 2) + (C + 1)) if probs else 0
     mufu_peak = n_sm * 16 * sm_hz
-    warp_instr = px / 64.0 * (T * 378.0 + 300.0) * (C / 19.0)        # pass loop (SASS count at C = 19) + ~300 per tile finalize
+    # 622.2 M warp instructions per launch measured by ncu at B = 8, 512 x 1024, C = 19, T = 20 (profiles/
+    # r1_fused_upsample_ncu_summary.txt; the pass loop alone is 378 SASS instructions per pass and pixel pair), scaled
+    # linearly in pixels, passes and classes
+    warp_instr = 622.24e6 * (px / (8.0 * 512 * 1024)) * (T * C) / (20.0 * 19.0)
     issue_peak = n_sm * 4 * sm_hz
     out["roofline"] = {"bound": "mufu", "algorithmic_ops": int(mufu_ops), "peak_ops_per_s": mufu_peak,
                        "achieved_ops_per_s": round(mufu_ops / (ms * 1e-3), 1), "frac": round(mufu_ops / (ms * 1e-3) / mufu_peak, 4),

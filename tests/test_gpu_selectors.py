@@ -4,6 +4,7 @@ import numpy as np
 import pytest
 import torch
 
+from deep_active_semantic_segmentation_b200 import synth
 from tests import fakes
 from tests import golden_util as G
 
@@ -450,3 +451,59 @@ def test_square_nms_leaves_the_callers_cuda_tensor_like_the_reference():
         got_sel, got_count = ActiveSelectionMCDropout.square_nms(t, 5, 6.2)
         assert (got_sel, got_count) == (want_sel, want_count)
         np.testing.assert_array_equal(t.cpu().numpy(), want_maps)
+
+
+def test_config1_live_dropout_model_under_dataparallel():
+    """BASELINE config 1 as the reference runs it (active_train.py:48,83-85,333; mc_dropout.py:175-178): a stochastic
+    nn.Module with live Dropout2d wrapped in nn.DataParallel - no replay.  A forward hook captures the logits of every
+    pass as the scorer saw them; the oracle on exactly those logits must give the selector's scores and ranking."""
+    N, T, C, S, bs, k = 6, 5, 21, 65, 4, 3
+
+    class SmallNet(torch.nn.Module):            # conv -> Dropout2d -> conv, like the decoder tail (models/decoder.py:35)
+        def __init__(self):
+            super().__init__()
+            torch.manual_seed(3)
+            self.body = torch.nn.Sequential(torch.nn.Conv2d(3, 16, 3, padding=1), torch.nn.ReLU(),
+                                            torch.nn.Dropout2d(0.25), torch.nn.Conv2d(16, C, 3, padding=1))
+
+        def forward(self, x):
+            return self.body(x)
+
+    net = SmallNet().cuda()
+    model = torch.nn.DataParallel(net, device_ids=[0]).eval()
+    seen = []
+    net.register_forward_hook(lambda m, i, o: seen.append(o.detach().clone()))
+    g = torch.Generator().manual_seed(9)
+    images = torch.rand((N, 3, S, S), generator=g)
+    labels = synth.pool_labels(5, list(range(N)), S, S, C, 8)
+
+    class DS(torch.utils.data.Dataset):
+        def __init__(self, env, paths, crop_size, include_labels=False):
+            self.paths = paths
+
+        def __len__(self):
+            return len(self.paths)
+
+        def __getitem__(self, i):
+            j = int(self.paths[i])
+            return {"image": images[j], "label": torch.from_numpy(labels[j])}
+
+    from deep_active_semantic_segmentation_b200.active_selection import base
+    base.paths_dataset.PathsDataset = DS            # (the autouse fixture restores it)
+    _set_T(T)
+    sel = _factory("variance", C, None, S, bs)
+    chosen = sel.get_vote_entropy_for_images(model, _paths(N), k)
+    assert not net.body[2].training                                   # model.eval() restored (mc_dropout.py:194)
+    assert len(seen) == T * -(-N // bs)
+    from oracle import restate as R
+    scores, pos = [], 0
+    for b0 in range(0, N, bs):
+        nb = min(bs, N - b0)
+        stack = torch.stack(seen[pos:pos + T], dim=1).cpu().numpy()   # [nb,T,C,S,S]
+        pos += T
+        assert not np.array_equal(stack[:, 0], stack[:, 1])           # dropout was live: passes differ
+        for i in range(nb):
+            scores.append(R.image_scores(R.mc_maps(stack[i], labels[b0 + i], C))["vote_entropy"])
+    np.testing.assert_allclose(sel.last_scores, scores, rtol=RTOL, atol=ATOL)
+    assert _idx(chosen) == R.rank_topk(scores, k, True)
+    assert max(scores) > 0
