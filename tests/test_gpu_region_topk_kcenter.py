@@ -323,3 +323,43 @@ def test_kcenter_baseline_size_filtered_equals_exact():
     assert p0.cpu().tolist() == p1.cpu().tolist() and torch.equal(m0, m1)
     exact, screened = flt.stats()
     assert exact < 0.25 * screened
+
+
+@pytest.mark.parametrize("descending", [True, False])
+def test_topk_records_and_merge_equal_the_unsharded_stable_ranking(descending):
+    """das_topk_records + das_topk_merge (the multi-GPU candidate exchange, here with the 'ranks' simulated by slicing):
+    every shard writes k record slots (padding behind a short shard, an EMPTY shard writes padding only), the gathered
+    table is merged on the device; the result must be the stable ranking of the whole pool - ties by global index."""
+    from deep_active_semantic_segmentation_b200 import ops
+    rng = np.random.default_rng(12)
+    n, k, W = 103, 17, 5
+    scores = np.round(rng.standard_normal(n), 1).astype(np.float32)     # many exact ties
+    scores[7] = scores[50] = scores[90] = scores.max() if descending else scores.min()   # a tie across shards at the top
+    bounds = [0, 40, 40, 41, 80, n]                                      # shard 1 is empty, shard 2 has one row (< k)
+    blocks = []
+    for r in range(W):
+        lo, hi = bounds[r], bounds[r + 1]
+        rec = ops.topk_records(torch.from_numpy(scores[lo:hi]).cuda(), k, descending, id_offset=lo)
+        assert rec.shape == (k, 2) and rec.dtype == torch.int64
+        s_loc, i_loc = ops.records_to_host(rec)
+        assert len(i_loc) == min(k, hi - lo)
+        assert i_loc.tolist() == [lo + j for j in R.rank_topk(scores[lo:hi].tolist(), k, descending)]
+        np.testing.assert_array_equal(s_loc, scores[i_loc])
+        blocks.append(rec)
+    merged = ops.topk_merge(torch.cat(blocks), k, descending)
+    ms, mi = ops.records_to_host(merged)
+    assert mi.tolist() == R.rank_topk(scores.tolist(), k, descending)
+    np.testing.assert_array_equal(ms, scores[mi])
+    # payload ids instead of positions (region candidates: flat pool indices, -1 = unused slot with a -inf score)
+    ids = torch.arange(1000, 1000 + n, dtype=torch.int64).cuda()
+    sc = torch.from_numpy(scores).cuda().clone()
+    sc[::9] = float("-inf")
+    ids[::9] = -1
+    rec = ops.topk_records(sc, 30, True, ids=ids)
+    s_p, i_p = ops.records_to_host(rec)
+    keep = [j for j in R.rank_topk(sc.cpu().tolist(), 30, True) if j % 9 != 0]
+    assert i_p.tolist() == [1000 + j for j in keep]
+    # fewer candidates than slots everywhere: the merge returns what exists, padding is dropped on the host
+    small = ops.topk_merge(torch.cat([ops.topk_records(torch.from_numpy(scores[:3]).cuda(), 8, descending),
+                                      ops.topk_records(torch.from_numpy(scores[3:5]).cuda(), 8, descending, id_offset=3)]), 8, descending)
+    assert ops.records_to_host(small)[1].tolist() == R.rank_topk(scores[:5].tolist(), 8, descending)
