@@ -63,6 +63,7 @@ _PROTOTYPES = {
     "das_suppress_rects": (_i, [_h, _vp, _i, _i, _i, _vp, _i, _vp]),
     "das_suppress_rects_host": (_i, [_h, _vp, _i, _i, _i, C.POINTER(C.c_int32), _i, _vp]),
     "das_add_maps": (_i, [_h, _vp, _vp, _sz, _vp]),
+    "das_add_gaussian_noise": (_i, [_h, _vp, _sz, _f, C.c_uint64, C.c_uint64, _vp, _vp]),
     "das_box_sum_workspace_bytes": (_i, [_i, _i, _i, _i, C.POINTER(_sz)]),
     "das_minmax_init": (_i, [_h, _vp, _vp]),
     "das_box_sum": (_i, [_h, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),

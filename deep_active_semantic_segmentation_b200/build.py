@@ -33,7 +33,7 @@ MC_RANGES = [(2, 9), (10, 16), (17, 20), (21, 24), (25, 28), (29, 32)]
 
 def _units():
     units = []
-    for name in ("handle", "mc_api", "region", "topk", "kcenter", "gram", "accuracy", "maxsubset"):
+    for name in ("handle", "mc_api", "region", "topk", "kcenter", "gram", "accuracy", "maxsubset", "noise"):
         units.append((name, os.path.join(CSRC, name + ".cu"), []))
     for lo, hi in MC_RANGES:
         units.append((f"mc_inst_{lo}_{hi}", os.path.join(CSRC, "mc_inst.cu"), [f"-DDAS_C_LO={lo}", f"-DDAS_C_HI={hi}"]))

@@ -238,6 +238,20 @@ def add_maps(a: torch.Tensor, b: torch.Tensor) -> None:
     check(_lib.load().das_add_maps(_h(a.device), _ptr(a), _ptr(b), a.numel(), _stream(a.device)), "das_add_maps")
 
 
+def add_gaussian_noise(x: torch.Tensor, sigma: float, seed: int, stream_id: int, out: torch.Tensor | None = None) -> torch.Tensor:
+    """x + sigma * N(0,1) drawn on the device (das_add_gaussian_noise, mc_noise.py:26-27); the noise is a pure function
+    of (seed, stream_id, element index).  `out` may be a reusable buffer of x's shape (or x itself)."""
+    x = _need_cuda(x, "x", torch.float32)
+    if out is None:
+        out = torch.empty_like(x)
+    elif not out.is_cuda or out.dtype != torch.float32 or not out.is_contiguous() or out.shape != x.shape:
+        raise DasError("add_gaussian_noise: `out` must be a contiguous CUDA float32 tensor of x's shape")
+    check(_lib.load().das_add_gaussian_noise(_h(x.device), _ptr(x), x.numel(), C.c_float(sigma), int(seed) & (2 ** 64 - 1),
+                                             int(stream_id) & (2 ** 64 - 1), _ptr(out), _stream(x.device)),
+          "das_add_gaussian_noise")
+    return out
+
+
 def new_minmax(device) -> torch.Tensor:
     mm = torch.empty(2, dtype=torch.float32, device=device)
     check(_lib.load().das_minmax_init(_h(mm.device), _ptr(mm), _stream(mm.device)), "das_minmax_init")

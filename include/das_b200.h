@@ -203,6 +203,14 @@ int das_suppress_rects(das_handle* h, float* maps, int B, int H, int W, const in
 int das_suppress_rects_host(das_handle* h, float* maps, int B, int H, int W, const int32_t* host_rects, int n,
                             void* stream);
 
+/* Input perturbation of the MC-noise selectors on the device:
+ *     noise = np.random.normal(0, 0.125, image_batch.shape); model(image_batch + noise)           mc_noise.py:26-27
+ * out[i] = x[i] + sigma * z[i], z ~ N(0,1) from Philox4x32-10 + Box-Muller, a pure function of (seed, stream_id, i):
+ * the same triple reproduces the same noise, different stream ids (one per pass) are independent streams.  One pass
+ * over the data (HBM bound); out may alias x. */
+int das_add_gaussian_noise(das_handle* h, const float* x, size_t n, float sigma, uint64_t seed, uint64_t stream_id,
+                           float* out, void* stream);
+
 /* a += b elementwise (combined noise + dropout vote entropy, mc_noise.py:141,165) */
 int das_add_maps(das_handle* h, float* a, const float* b, size_t n, void* stream);
 

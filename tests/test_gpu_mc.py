@@ -512,3 +512,38 @@ def test_two_devices_in_one_process():
         assert int(key[1].item()) == want[0]
         picks, _ = ops.kcenter_greedy(f, [0, 1, 2], 12)
         assert picks.cpu().tolist() == want
+
+
+def test_device_gaussian_noise_statistics_and_reproducibility():
+    """das_add_gaussian_noise (mc_noise.py:26-27 on the device): N(0, sigma) statistics, a pure function of
+    (seed, stream id, element), independent streams, ragged / unaligned sizes, in place."""
+    ops = _ops()
+    n = 1 << 22
+    x = torch.zeros(n, device="cuda")
+    z = ops.add_gaussian_noise(x, 1.0, seed=1234, stream_id=7)
+    m, s = float(z.mean()), float(z.std())
+    assert abs(m) < 5 / np.sqrt(n) and abs(s - 1) < 5 / np.sqrt(2 * n)
+    zz = z.double()
+    assert abs(float((zz ** 3).mean())) < 0.01 and abs(float((zz ** 4).mean()) - 3.0) < 0.02      # skewness 0, kurtosis 3
+    assert 4.5 < float(z.abs().max()) < 7.0
+    # tail mass like a Gaussian's: P(|z| > 2) = 4.55 %, P(|z| > 3) = 0.27 %
+    assert abs(float((z.abs() > 2).float().mean()) - 0.0455) < 0.001 and abs(float((z.abs() > 3).float().mean()) - 0.0027) < 0.0003
+    # neighbouring elements / the four outputs of one counter are uncorrelated
+    for lag in (1, 2, 3, 4, 1024):
+        assert abs(float((z[:-lag] * z[lag:]).mean())) < 6 / np.sqrt(n)
+    assert torch.equal(z, ops.add_gaussian_noise(x, 1.0, seed=1234, stream_id=7))                   # reproducible
+    z2 = ops.add_gaussian_noise(x, 1.0, seed=1234, stream_id=8)
+    z3 = ops.add_gaussian_noise(x, 1.0, seed=1235, stream_id=7)
+    for other in (z2, z3):
+        assert not torch.equal(z, other) and abs(float((z * other).mean())) < 6 / np.sqrt(n)       # independent
+    # x + sigma * z exactly (fma), any size / alignment, in place
+    base = torch.randn(1003, device="cuda")
+    y = ops.add_gaussian_noise(base, 0.125, seed=5, stream_id=1)
+    z1 = ops.add_gaussian_noise(torch.zeros(1003, device="cuda"), 1.0, seed=5, stream_id=1)
+    torch.testing.assert_close(y, base + 0.125 * z1, rtol=0, atol=2e-7)
+    odd = base[1:1000]                                                   # 4-byte aligned only
+    y_odd = ops.add_gaussian_noise(odd.contiguous(), 0.125, seed=5, stream_id=1)
+    torch.testing.assert_close(y_odd, odd + 0.125 * z1[:999], rtol=0, atol=2e-7)
+    buf = base.clone()
+    assert ops.add_gaussian_noise(buf, 0.125, seed=5, stream_id=1, out=buf).data_ptr() == buf.data_ptr()
+    assert torch.equal(buf, y)
