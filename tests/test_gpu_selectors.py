@@ -507,3 +507,78 @@ def test_config1_live_dropout_model_under_dataparallel():
     np.testing.assert_allclose(sel.last_scores, scores, rtol=RTOL, atol=ATOL)
     assert _idx(chosen) == R.rank_topk(scores, k, True)
     assert max(scores) > 0
+
+
+def test_config4_selector_is_ceal_at_one_pass_and_the_oracle_at_many(monkeypatch):
+    """ActiveSelectionMCNoise.get_mc_scores_for_images_with_input_noise (BASELINE config 4, composed: mc_noise.py:26-27 +
+    ceal.py): with one pass and sigma = 0 it must reproduce the reference's CEAL goldens; with T passes of real input
+    noise its scores are the restatement's on exactly the logits the model produced."""
+    from deep_active_semantic_segmentation_b200.active_selection import mc_noise
+    g = G.load("mc_small")
+    seed, N, T, C, H, W, block, k, bs = (int(v) for v in g["meta"])
+    logits, labels = G.pool_from_meta(seed, N, T, C, H, W, block, g["logits_sha"])
+    pool = fakes.Pool(logits, labels)
+    _set_T(1)
+    monkeypatch.setattr(mc_noise, "INPUT_NOISE_SIGMA", 0.0)
+    sel = _factory("noise_image", C, pool, H, bs)
+    for score, key, desc in (("pred_entropy", "ceal_entropy", True), ("confidence", "ceal_conf", False), ("margin", "ceal_margin", False)):
+        chosen, allv = sel.get_mc_scores_for_images_with_input_noise(fakes.ReplayModel(pool), _paths(N), k, score=score)
+        assert _idx(chosen) == g[key + "_selected"].tolist(), score
+        np.testing.assert_allclose(allv[score], g[key], rtol=RTOL, atol=ATOL)
+        np.testing.assert_allclose(sel.last_scores, g[key], rtol=RTOL, atol=ATOL)
+    with pytest.raises(NotImplementedError):
+        sel.get_mc_scores_for_images_with_input_noise(fakes.ReplayModel(pool), _paths(N), k, score="nope")
+    monkeypatch.undo()
+
+    # T passes with the real sigma through a model whose logits depend on its (noisy) input
+    Tn, Cn, S = 6, 5, 40
+    proj = torch.linspace(-3, 3, Cn * 3).reshape(Cn, 3, 1, 1).cuda()
+
+    class Probe(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.drop = torch.nn.Dropout2d(0.25)
+            self.out = []
+
+        def forward(self, x):
+            y = torch.nn.functional.conv2d(x, proj)
+            self.out.append(y.detach().clone())
+            return y
+
+    gen = torch.Generator().manual_seed(4)
+    images = torch.rand((5, 3, S, S), generator=gen)
+    lab = synth.pool_labels(6, list(range(5)), S, S, Cn, 8)
+
+    class DS(torch.utils.data.Dataset):
+        def __init__(self, env, paths, crop_size, include_labels=False):
+            self.paths = paths
+
+        def __len__(self):
+            return len(self.paths)
+
+        def __getitem__(self, i):
+            j = int(self.paths[i])
+            return {"image": images[j], "label": torch.from_numpy(lab[j])}
+
+    from deep_active_semantic_segmentation_b200.active_selection import base
+    base.paths_dataset.PathsDataset = DS
+    _set_T(Tn)
+    sel = _factory("noise_image", Cn, None, S, 2)
+    model = Probe().cuda().eval()
+    chosen, allv = sel.get_mc_scores_for_images_with_input_noise(model, _paths(5), 3, score="margin")
+    assert len(model.out) == Tn * 3 and not model.drop.training
+    from oracle import restate as R
+    want = {kk: [] for kk in R.SCORE_NAMES}
+    pos = 0
+    for b0 in range(0, 5, 2):
+        nb = min(2, 5 - b0)
+        stack = torch.stack(model.out[pos:pos + Tn], dim=1).cpu().numpy()
+        pos += Tn
+        assert not np.array_equal(stack[:, 0], stack[:, 1])            # fresh noise per pass
+        for i in range(nb):
+            sc = R.image_scores(R.mc_maps(stack[i], lab[b0 + i], Cn))
+            for kk in want:
+                want[kk].append(sc[kk])
+    for kk in ("pred_entropy", "confidence", "margin", "vote_entropy", "expected_entropy"):
+        np.testing.assert_allclose(allv[kk], want[kk], rtol=RTOL, atol=1e-6, err_msg=kk)
+    assert _idx(chosen) == R.rank_topk(want["margin"], 3, False)        # margin ranks ascending (ceal.py:97)
