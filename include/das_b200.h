@@ -65,7 +65,12 @@ enum {
     DAS_OPT_MC_UP_WARPS = 2,   /* DAS_MC_UP_WARPS  consumer warps of the fused-upsample kernel: 0 = auto, 4 or 15          */
     DAS_OPT_GEMM_2CTA = 3,     /* DAS_GEMM_2CTA    1: CTA-pair tcgen05 distance GEMM (default), 0: one CTA per tile       */
     DAS_OPT_KC_CLUSTER = 4,    /* DAS_KC_CLUSTER   1: k-center loop inside one thread-block cluster (default), 0: chain   */
-    DAS_OPT_MC_L2_PERSIST = 5, /* DAS_MC_L2_PERSIST 1: streaming accumulators pinned in L2 when they fit (default), 0: off */
+    DAS_OPT_MC_L2_PERSIST = 5, /* DAS_MC_L2_PERSIST 1: streaming accumulators pinned in L2 when they fit (default), 0: off.
+                                * Streaming launches (das_mc_accumulate, das_mc_finalize, a fused last group) then carry an
+                                * access-policy window over the head of the state, and the first of them raises the
+                                * device's persisting-L2 limit to its maximum; lines stay "persisting" until other
+                                * persisting traffic replaces them or the application calls
+                                * cudaCtxResetPersistingL2Cache().  The single-shot path never touches any of this. */
     DAS_OPT_COUNT = 6
 };
 
