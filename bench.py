@@ -65,6 +65,17 @@ def parse():
     return ap.parse_args()
 
 
+def workload_config(args, world):
+    """The `config` of the JSON line - identical for both arms (--impl b200 / reference) of the same command line."""
+    B, G = args.batch, max(1, min(args.pass_group, T))
+    return {"workload": WORKLOAD, "pool_images": POOL_IMAGES, "H": H, "W": W, "classes": C, "mc_passes": T,
+            "batch_images_per_step": B, "pass_group": G, "topk": TOPK, "mode": args.mode,
+            "scores": {"full": "vote_entropy+pred_entropy+bald+confidence+margin", "votes": "vote_entropy",
+                       "probs": "pred_entropy+bald+confidence+margin"}[args.mode],
+            "sharding": f"by image, {world} rank(s), candidate all-gather only",
+            "l2": f"inputs {T * B * C * H * W * 4 / 1e9:.2f} GB per step >> 126 MB L2 (no flush needed)"}
+
+
 def peaks_sm_mhz():
     return measured_peaks()[0].get("sm_max_mhz", 1965.0)
 
@@ -309,12 +320,7 @@ def run_b200(args):
             "metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm,
             "ms_per_step": round(elapsed_ms / K, 4), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "pool_images": POOL_IMAGES, "H": H, "W": W, "classes": C, "mc_passes": T,
-                       "batch_images_per_step": B, "pass_group": G, "topk": TOPK, "mode": args.mode,
-                       "scores": {"full": "vote_entropy+pred_entropy+bald+confidence+margin", "votes": "vote_entropy",
-                                  "probs": "pred_entropy+bald+confidence+margin"}[args.mode],
-                       "sharding": f"by image, {world} rank(s), candidate all-gather only",
-                       "l2": f"inputs {T * B * C * H * W * 4 / 1e9:.2f} GB per step >> 126 MB L2 (no flush needed)"},
+            "config": workload_config(args, world),
             "roofline": roofline, "cpu_baseline": cpu, "torch_gpu_baseline": torch_gpu, "e2e": e2e,
             "fused_upsample_variant": fused_up, "pass_group_sweep": sweep, "configs": configs,
             "gpu_launches": int(launches), "clocks": clocks,
@@ -874,7 +880,7 @@ def run_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": round(value, 4), "unit": UNIT, "n_gpus": args.gpus, "steps": K,
             "warmup": Wm, "ms_per_step": round(dt / K * 1e3, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "pool_images": POOL_IMAGES, "H": H, "W": W, "classes": C, "mc_passes": T},
+            "config": workload_config(args, max(1, int(args.gpus))),     # the same dict as the b200 arm of this N
             "cpu_baseline": {"value": round(value, 4), "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": round(value, 4), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
