@@ -8,8 +8,8 @@
 #include "mc_kernels.cuh"
 
 namespace das {
-int g_last_cuda_error = 0;
-unsigned long long g_launch_count = 0;
+thread_local int g_last_cuda_error = 0;
+std::atomic<unsigned long long> g_launch_count{0};
 }  // namespace das
 using namespace das;
 
