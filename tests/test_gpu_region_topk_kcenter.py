@@ -363,3 +363,27 @@ def test_topk_records_and_merge_equal_the_unsharded_stable_ranking(descending):
     small = ops.topk_merge(torch.cat([ops.topk_records(torch.from_numpy(scores[:3]).cuda(), 8, descending),
                                       ops.topk_records(torch.from_numpy(scores[3:5]).cuda(), 8, descending, id_offset=3)]), 8, descending)
     assert ops.records_to_host(small)[1].tolist() == R.rank_topk(scores[:5].tolist(), 8, descending)
+
+
+def test_suppress_rects_many_host_records_and_device_records():
+    """das_suppress_rects_host passes the records in the kernel parameters, 128 per launch: 300 records (three launches),
+    clipped and degenerate rectangles included, must equal the Python slices of mc_dropout.py:110-121; device records
+    (das_suppress_rects) give the same."""
+    from deep_active_semantic_segmentation_b200 import ops
+    rng = np.random.default_rng(21)
+    B, H, W = 5, 37, 53
+    m = rng.random((B, H, W)).astype(np.float32) + 1
+    rects = [(int(rng.integers(0, B)), int(rng.integers(0, H + 5)), int(rng.integers(0, W + 5)), int(rng.integers(0, 9)),
+              int(rng.integers(0, 9))) for _ in range(300)]
+    want = m.copy()
+    for (i, r, c, h, w) in rects:
+        want[i, r:r + h, c:c + w] = 0
+    t = torch.from_numpy(m.copy()).cuda()
+    ops.suppress_rects(t, rects)
+    np.testing.assert_array_equal(t.cpu().numpy(), want)
+    t2 = torch.from_numpy(m.copy()).cuda()
+    ops.suppress_rects(t2, torch.tensor(rects, dtype=torch.int32).cuda())
+    np.testing.assert_array_equal(t2.cpu().numpy(), want)
+    t3 = torch.from_numpy(m.copy()).cuda()
+    ops.suppress_rects(t3, [])
+    np.testing.assert_array_equal(t3.cpu().numpy(), m)
