@@ -450,11 +450,14 @@ def config_records(args, world, rank, dev, peaks):
         from deep_active_semantic_segmentation_b200 import ops
         ops.KCenterFilter(feats)
         torch.cuda.synchronize()
-        ev[0].record()
-        ops.KCenterFilter(feats)
-        ev[1].record()
-        torch.cuda.synchronize()
-        gemm_ms = ev[0].elapsed_time(ev[1])
+        gemm_runs = []
+        for _ in range(3):      # allocation of the 0.44 GB table + memset + bf16 / norm preparation + the GEMM; best of three
+            ev[0].record()
+            ops.KCenterFilter(feats)
+            ev[1].record()
+            torch.cuda.synchronize()
+            gemm_runs.append(ev[0].elapsed_time(ev[1]))
+        gemm_ms = min(gemm_runs)
         flops = 2.0 * N5 * N5 * (-(-D5 // 64) * 64)
         tf = flops / (gemm_ms * 1e-3) / 1e12
         out["config5_coreset_kcenter"] = {
