@@ -298,3 +298,17 @@ def test_selections_txt_is_what_the_reference_tools_read_and_write(tmp_path):
     selections.write_selections(b, own_paths[:-1], run=0)
     with pytest.raises(ValueError):
         selections.compare_selections(a, b)
+
+
+def test_numa_binding_helper_is_harmless_without_topology():
+    """dist.bind_to_gpu_numa_node never raises: without a visible PCI / NUMA topology (this container: no GPU at all) it
+    reports why and leaves the affinity of the process alone."""
+    from deep_active_semantic_segmentation_b200 import dist
+    before = os.sched_getaffinity(0)
+    info = dist.bind_to_gpu_numa_node(0)
+    assert info["device"] == 0 and isinstance(info["bound"], bool)
+    if not info["bound"]:
+        assert os.sched_getaffinity(0) == before
+    os.sched_setaffinity(0, before)
+    from deep_active_semantic_segmentation_b200 import prefetch
+    assert 1 <= prefetch.copy_threads() <= 8
