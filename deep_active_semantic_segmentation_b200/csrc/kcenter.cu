@@ -12,6 +12,7 @@
 // written to min_d2 and the picks are bit-identical to the unfiltered path.
 #include <math.h>
 #include <stdlib.h>
+#include <string.h>
 
 #include "das_common.cuh"
 #include "gram.cuh"
@@ -367,11 +368,11 @@ __global__ void __launch_bounds__(kKcThreads) kcenter_fstep_kernel(const float* 
 
 // ---- whole greedy loop in ONE thread-block cluster (single-GPU path with a filter) -----------------
 // 500 dependent steps of a few microseconds each are launch-latency bound as a chain of kernels (~9 us per
-// step measured).  Here 8 CTAs x 1024 threads of one cluster keep min_d2 and the row norms in REGISTERS
+// step measured).  Here 4 or 8 CTAs x 1024 threads of one cluster keep min_d2 and the row norms in REGISTERS
 // (up to kClRows rows per thread), stage the centre row in shared memory, exchange each CTA's arg-max
 // through distributed shared memory (st.shared::cluster) and meet at one hardware cluster barrier per
 // step: no kernel boundary, no global-memory round trip for the arg-max.
-constexpr int kClCtas = 8;
+constexpr int kClCtasMax = 8;   // CTAs per cluster: 4 or 8 (the portable maximum), chosen from N at launch
 constexpr int kClThreads = 1024;
 constexpr int kClWarps = kClThreads / 32;
 constexpr int kClRows = 4;  // rows per thread -> N <= 8 * 1024 * 4 = 32768
@@ -392,8 +393,8 @@ __device__ __forceinline__ void cluster_barrier() {
     asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 
-template <bool VEC4>
-__global__ void __cluster_dims__(kClCtas, 1, 1) __launch_bounds__(kClThreads, 1)
+template <bool VEC4, int kClCtas>
+__global__ void __launch_bounds__(kClThreads, 1)
     kcenter_cluster_kernel(const float* __restrict__ feats, int N, int D, double* __restrict__ min_d2, int K,
                            int32_t* __restrict__ picks, double* __restrict__ min_d_out, const KcFilter f, int stage_centre) {
     extern __shared__ float4 cl_dyn[];  // [centre row][wl_val f64 x 4 quarters x 4096][wl_row i32 x 4096]
@@ -654,6 +655,32 @@ static int kc_launch_fstep(bool v4, int grid, cudaStream_t st, const float* feat
     return DAS_OK;
 }
 
+// One thread-block cluster of NC CTAs (cluster dimension as a launch attribute) runs the whole greedy loop.
+template <bool VEC4, int NC>
+static int kc_launch_cluster_t(size_t smem, cudaStream_t st, const float* feats, int N, int D, double* d2, int K, int32_t* picks,
+                               double* min_d, const KcFilter& f, int stage_centre) {
+    auto kernel = kcenter_cluster_kernel<VEC4, NC>;
+    DAS_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(NC), cfg.blockDim = dim3(kClThreads), cfg.dynamicSmemBytes = smem, cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = NC, attr[0].val.clusterDim.y = 1, attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr, cfg.numAttrs = 1;
+    DAS_CUDA(cudaLaunchKernelEx(&cfg, kernel, feats, N, D, d2, K, picks, min_d, f, stage_centre));
+    g_launch_count.fetch_add(1, std::memory_order_relaxed);
+    return DAS_OK;
+}
+static int kc_launch_cluster(bool v4, int nc, size_t smem, cudaStream_t st, const float* feats, int N, int D, double* d2, int K,
+                             int32_t* picks, double* min_d, const KcFilter& f, int stage_centre) {
+    if (nc == 4)
+        return v4 ? kc_launch_cluster_t<true, 4>(smem, st, feats, N, D, d2, K, picks, min_d, f, stage_centre)
+                  : kc_launch_cluster_t<false, 4>(smem, st, feats, N, D, d2, K, picks, min_d, f, stage_centre);
+    return v4 ? kc_launch_cluster_t<true, 8>(smem, st, feats, N, D, d2, K, picks, min_d, f, stage_centre)
+              : kc_launch_cluster_t<false, 8>(smem, st, feats, N, D, d2, K, picks, min_d, f, stage_centre);
+}
+
 }  // namespace das
 
 using namespace das;
@@ -737,22 +764,14 @@ int das_kcenter_greedy(das_handle* h, const float* feats, int N, int D, const in
         int grid = kc_grid(h, N);
         rc = kc_launch_finit(v4, grid, st, feats, D, 0, N, centers, L, w.d2, w.best[0], f);
         if (rc != DAS_OK) return rc;
-        if (N <= kClCtas * kClThreads * kClRows && h->opt[DAS_OPT_KC_CLUSTER]) {
-            // the whole loop inside one thread-block cluster
+        if (N <= kClCtasMax * kClThreads * kClRows && h->opt[DAS_OPT_KC_CLUSTER]) {
             const size_t row_bytes = (size_t)D * sizeof(float);
             const int stage_centre = row_bytes <= 64 * 1024 ? 1 : 0;  // + 144 KB of work-list tables <= 227 KB
             const size_t smem = (stage_centre ? align_up(row_bytes, 16) : 0) + (size_t)kClThreads * kClRows * (4 * 8 + 4);
-            if (v4) {
-                DAS_CUDA(cudaFuncSetAttribute(kcenter_cluster_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                DAS_LAUNCH((kcenter_cluster_kernel<true>), kClCtas, kClThreads, smem, st, feats, N, D, w.d2, K, picks, min_d, f,
-                           stage_centre);
-            } else {
-                DAS_CUDA(cudaFuncSetAttribute(kcenter_cluster_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                DAS_LAUNCH((kcenter_cluster_kernel<false>), kClCtas, kClThreads, smem, st, feats, N, D, w.d2, K, picks, min_d, f,
-                           stage_centre);
-            }
-            DAS_CHECK_LAUNCH();
-            return DAS_OK;
+            // the smallest cluster that holds the rows: 4 CTAs up to 16 384 rows (measured 2.94 ms against 3.03 ms with 8
+            // and 3.57 ms with a non-portable 16-CTA cluster at N = 10 000 - every record more costs exchange latency)
+            const int nc = N <= 4 * kClThreads * kClRows ? 4 : 8;
+            return kc_launch_cluster(v4, nc, smem, st, feats, N, D, w.d2, K, picks, min_d, f, stage_centre);
         }
         int n_prev = grid;
         grid = kc_fgrid(h, N);
