@@ -330,3 +330,71 @@ def test_upsampled_scoring_matches_reference(name):
     assert R.rank_topk(ent, k, True) == g["ceal_entropy_selected"].tolist()
     assert R.rank_topk(conf, k, False) == g["ceal_conf_selected"].tolist()
     assert R.rank_topk(marg, k, False) == g["ceal_margin_selected"].tolist()
+
+
+@pytest.mark.skipif(not __import__("os").path.isdir("/root/reference/models"), reason="needs the reference tree (build container only)")
+def test_restatement_on_the_reference_deeplab_mobilenet_with_live_dropout():
+    """BASELINE config 1 as written: the reference's own DataParallel-style DeepLab-MobileNet (pretrained=False, seed 0),
+    Dropout2d live (mc_dropout.py:175-178), T = 5, 513 x 513, 21 classes, through the reference's selector on the CPU.
+    The logits of every pass are captured with a forward hook; the restatement on exactly those logits must give the
+    reference's scores and ranking (2 images keep it to ~10 s of CPU)."""
+    import torch
+    from oracle import ref_shim
+    ref = ref_shim.load_reference()
+    from models.deeplab import DeepLab          # reference model, unmodified
+
+    N, T, C, S, bs = 2, 5, 21, 513, 2
+    torch.manual_seed(0)
+    net = DeepLab(num_classes=C, backbone="mobilenet", output_stride=16, sync_bn=False, freeze_bn=False, pretrained=False)
+    net.eval()
+    seen = []
+    net.register_forward_hook(lambda m, i, o: seen.append(o.detach().clone()))
+    g = torch.Generator().manual_seed(1)
+    images = torch.randn((N, 3, S, S), generator=g)
+    from deep_active_semantic_segmentation_b200 import synth
+    labels = synth.pool_labels(9, list(range(N)), S, S, C, 32)
+
+    class DS:
+        def __init__(self, env, paths, crop_size, include_labels=False):
+            self.paths = paths
+
+        def __len__(self):
+            return len(self.paths)
+
+        def __getitem__(self, i):
+            j = int(self.paths[i])
+            return {"image": images[j], "label": torch.from_numpy(labels[j])}
+
+    class Wrapper(torch.nn.Module):             # what nn.DataParallel looks like to the selector: .module + call
+        def __init__(self, m):
+            super().__init__()
+            self.module = m
+
+        def forward(self, x):
+            return self.module(x)
+
+    old_ds, old_T = ref.paths_dataset.PathsDataset, ref.constants.MC_STEPS
+    ref.paths_dataset.PathsDataset, ref.constants.MC_STEPS = DS, T
+    captured = {}
+    import builtins
+    real_sorted = builtins.sorted
+
+    def spy(iterable, key=None, reverse=False):
+        items = list(iterable)
+        captured["scores"] = [float(x[0]) for x in items]
+        return real_sorted(items, key=key, reverse=reverse)
+
+    ref.mc_dropout.sorted = spy
+    try:
+        sel = ref.active_selection.get_active_selection_class("variance", C, None, S, bs)
+        chosen = sel.get_vote_entropy_for_images(Wrapper(net), [str(i) for i in range(N)], N)
+    finally:
+        del ref.mc_dropout.sorted
+        ref.paths_dataset.PathsDataset, ref.constants.MC_STEPS = old_ds, old_T
+    assert len(seen) == T and seen[0].shape == (N, C, S, S)
+    assert not torch.equal(seen[0], seen[1])                                  # the decoder / ASPP Dropout2d were live
+    stack = torch.stack(seen, dim=1).numpy()                                  # [N,T,C,S,S]
+    mine = [R.image_scores(R.mc_maps(stack[i], labels[i], C))["vote_entropy"] for i in range(N)]
+    np.testing.assert_allclose(mine, captured["scores"], rtol=RTOL, atol=1e-7)
+    assert [int(p) for p in chosen] == R.rank_topk(mine, N, True)
+    assert not any(m.training for m in net.modules() if isinstance(m, torch.nn.Dropout2d))   # model.eval() restored
