@@ -582,3 +582,26 @@ def test_config4_selector_is_ceal_at_one_pass_and_the_oracle_at_many(monkeypatch
     for kk in ("pred_entropy", "confidence", "margin", "vote_entropy", "expected_entropy"):
         np.testing.assert_allclose(allv[kk], want[kk], rtol=RTOL, atol=1e-6, err_msg=kk)
     assert _idx(chosen) == R.rank_topk(want["margin"], 3, False)        # margin ranks ascending (ceal.py:97)
+
+
+def test_selection_count_above_the_topk_kernel_limit_falls_back_to_a_stable_host_sort():
+    """The reference's sorted()[:k] has no limit; one K3 launch ranks at most 4096 winners.  k = 4500 of 5000 tiny images
+    must still be the stable ranking of the pool."""
+    from oracle import restate as R
+    N, C, S, bs, k = 5000, 3, 4, 500, 4500
+    rng = np.random.default_rng(17)
+    logits = np.round(rng.standard_normal((N, 1, C, S, S)), 1).astype(np.float32)     # coarse values: many tied scores
+    logits[100:200] = logits[300:400]                                                  # and exact duplicates
+    labels = np.zeros((N, S, S), dtype=np.float32)
+    pool = fakes.Pool(logits, labels)
+    _set_T(1)
+    sel = _factory("ceal_confidence", C, pool, S, bs)
+    chosen = sel.get_least_confident_samples(fakes.ReplayModel(pool), _paths(N), k)
+    want_scores = [R.image_scores(R.mc_maps(logits[i], labels[i], C))["confidence"] for i in range(N)]
+    np.testing.assert_allclose(sel.last_scores, want_scores, rtol=RTOL, atol=ATOL)
+    got = _idx(chosen)
+    assert len(got) == k and len(set(got)) == k
+    # the mirror ranks ITS float32 scores; ties (duplicates) must come out in index order like Python's stable sort
+    assert got == R.rank_topk(list(sel.last_scores), k, False)
+    small = sel.get_least_confident_samples(fakes.ReplayModel(pool), _paths(N), 50)
+    assert _idx(small) == got[:50]                                                     # device path agrees with the host path
