@@ -168,29 +168,58 @@ __global__ void minmax_normalise_kernel(float* x, size_t n, const float* minmax)
 // Image-local greedy NMS (mc_dropout.py:87-106 restricted to one image): one CTA per image.
 // argmax key = (orderable(score) << 32) | ~flat_index  -> max key == first flat index among the
 // maximal scores, exactly torch's argmax tie rule.
+//
+// The reference re-scans the WHOLE pool for every pick (mc_dropout.py:91).  Here the map is covered by 32 x 32 tiles
+// whose arg-max keys live in shared memory: a pick is the arg-max over the tile keys; zeroing its [r-R, r+R) x [c-R, c+R)
+// window only invalidates the tiles the window touches, and of those the ones it covers completely need no re-scan
+// (all zero: key of 0.0 at the tile's first element).  Per pick: 64 K cells zeroed + ~32 edge tiles re-read instead of
+// the 345 K-cell map (config 3: 385 x 897, R = 128) - 3.7x less traffic per image, same picks bit for bit.
 // ---------------------------------------------------------------------------------------------
 constexpr int kNmsThreads = 512;
+constexpr int kNmsTile = 32;
+
+__device__ __forceinline__ unsigned long long nms_key(float v, int flat) {
+    return ((unsigned long long)float_orderable(v) << 32) | (uint32_t)(~(uint32_t)flat);
+}
+// arg-max key of tile (tr, tc) by one warp: lane = column, coalesced 128-byte row segments
+__device__ __forceinline__ unsigned long long nms_tile_scan(const float* m, int H2, int W2, int tr, int tc, int lane) {
+    const int c = tc * kNmsTile + lane;
+    const int r_end = min((tr + 1) * kNmsTile, H2);
+    unsigned long long best = 0ull;
+    if (c < W2)
+        for (int r = tr * kNmsTile; r < r_end; ++r) {
+            const int flat = r * W2 + c;
+            const unsigned long long key = nms_key(m[flat], flat);
+            best = key > best ? key : best;
+        }
+    return warp_max_u64(best);
+}
+
 __global__ void __launch_bounds__(kNmsThreads) nms_sequences_kernel(float* score_maps, int H2, int W2, int R, int kmax,
                                                                     float stop, float* cand_score, int32_t* cand_rc,
                                                                     int32_t* cand_count, long long image_offset,
                                                                     int64_t* cand_flat) {
+    extern __shared__ unsigned long long tile_key[];  // [TH * TW]
     __shared__ unsigned long long wbest[kNmsThreads / 32];
     __shared__ unsigned long long best_s;
     const int img = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    constexpr int NW = kNmsThreads / 32;
     float* m = score_maps + (size_t)img * H2 * W2;
-    const int n = H2 * W2;
+    const int TH = (H2 + kNmsTile - 1) / kNmsTile, TW = (W2 + kNmsTile - 1) / kNmsTile, nt = TH * TW;
+    for (int t = wid; t < nt; t += NW) {
+        const unsigned long long k = nms_tile_scan(m, H2, W2, t / TW, t % TW, lane);
+        if (lane == 0) tile_key[t] = k;
+    }
+    __syncthreads();
     int picks = 0;
     while (picks < kmax) {
         unsigned long long best = 0ull;
-        for (int i = tid; i < n; i += kNmsThreads) {
-            const unsigned long long key = ((unsigned long long)float_orderable(m[i]) << 32) | (uint32_t)(~(uint32_t)i);
-            best = key > best ? key : best;
-        }
+        for (int t = tid; t < nt; t += kNmsThreads) best = tile_key[t] > best ? tile_key[t] : best;
         best = warp_max_u64(best);
         if (lane == 0) wbest[wid] = best;
         __syncthreads();
         if (tid == 0) {
-            for (int w = 1; w < kNmsThreads / 32; ++w) best = wbest[w] > best ? wbest[w] : best;
+            for (int w = 1; w < NW; ++w) best = wbest[w] > best ? wbest[w] : best;
             best_s = best;
         }
         __syncthreads();
@@ -210,6 +239,18 @@ __global__ void __launch_bounds__(kNmsThreads) nms_sequences_kernel(float* score
         const int r0 = max(0, r - R), r1 = min(H2, r + R), c0 = max(0, c - R), c1 = min(W2, c + R);
         const int w = c1 - c0, cells = (r1 - r0) * w;
         for (int i = tid; i < cells; i += kNmsThreads) m[(size_t)(r0 + i / w) * W2 + c0 + i % w] = 0.f;
+        __syncthreads();  // the zeroed window is visible to the re-scans below
+        // refresh the keys of the tiles the window touches
+        const int tr_lo = r0 / kNmsTile, tr_hi = (r1 - 1) / kNmsTile, tc_lo = c0 / kNmsTile, tc_hi = (c1 - 1) / kNmsTile;
+        const int tcols = tc_hi - tc_lo + 1, touched = (tr_hi - tr_lo + 1) * tcols;
+        for (int k = wid; k < touched; k += NW) {
+            const int tr = tr_lo + k / tcols, tc = tc_lo + k % tcols;
+            const int tr0 = tr * kNmsTile, tc0 = tc * kNmsTile;
+            const bool inside = tr0 >= r0 && min(tr0 + kNmsTile, H2) <= r1 && tc0 >= c0 && min(tc0 + kNmsTile, W2) <= c1;
+            // completely inside the window: every cell is +0.0, the first flat index is the tile's top-left cell
+            const unsigned long long key = inside ? nms_key(0.f, tr0 * W2 + tc0) : nms_tile_scan(m, H2, W2, tr, tc, lane);
+            if (lane == 0) tile_key[tr * TW + tc] = key;
+        }
         __syncthreads();
     }
     if (tid == 0) cand_count[img] = picks;
@@ -311,7 +352,12 @@ int das_nms_sequences(das_handle* h, float* score_maps, int N, int H2, int W2, i
     if (N <= 0 || H2 <= 0 || W2 <= 0 || R <= 0 || kmax <= 0) return DAS_ERR_INVALID_ARG;
     if ((long long)H2 * W2 > 0x7fffffffLL) return DAS_ERR_UNSUPPORTED;
     if (image_offset < 0) return DAS_ERR_INVALID_ARG;
-    DAS_LAUNCH(nms_sequences_kernel, N, kNmsThreads, 0, (cudaStream_t)stream, score_maps, H2, W2, R, kmax, stop,
+    const size_t tiles = (size_t)((H2 + kNmsTile - 1) / kNmsTile) * ((W2 + kNmsTile - 1) / kNmsTile);
+    const size_t smem = tiles * sizeof(unsigned long long);     // one arg-max key per 32 x 32 tile
+    if (smem > 200 * 1024) return DAS_ERR_UNSUPPORTED;           // maps beyond ~5000 x 5000
+    if (smem > 48 * 1024)
+        DAS_CUDA(cudaFuncSetAttribute(nms_sequences_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    DAS_LAUNCH(nms_sequences_kernel, N, kNmsThreads, smem, (cudaStream_t)stream, score_maps, H2, W2, R, kmax, stop,
                cand_score, cand_rc, cand_count, image_offset, cand_flat);
     DAS_CHECK_LAUNCH();
     return DAS_OK;
