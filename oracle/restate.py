@@ -303,27 +303,36 @@ def region_selection(ve_maps, existing_regions, R: int, selection_size: int, bas
 # core-set
 # --------------------------------------------------------------------------------------
 
+def _euclidean_f64(x: np.ndarray, xx: np.ndarray, y: np.ndarray) -> np.ndarray:
+    """The formula of euclidean_to on float64 rows x with their squared norms xx already at hand."""
+    d2 = xx[:, None] + (y * y).sum(1)[None, :] - 2.0 * (x @ y.T)
+    np.maximum(d2, 0, out=d2)
+    return np.sqrt(d2)
+
+
 def euclidean_to(features: np.ndarray, centres: np.ndarray) -> np.ndarray:
     """sklearn pairwise_distances(metric='euclidean') on float64 input (core_set.py:34):
     sqrt(max(|x|^2 + |y|^2 - 2 x.y, 0)).  scikit-learn is a third-party dependency of the
     reference (unpinned there; 1.9.0 in this container) - this is its published formula."""
     x = np.asarray(features, dtype=np.float64)
     y = np.asarray(centres, dtype=np.float64)
-    d2 = (x * x).sum(1)[:, None] + (y * y).sum(1)[None, :] - 2.0 * (x @ y.T)
-    np.maximum(d2, 0, out=d2)
-    return np.sqrt(d2)
+    return _euclidean_f64(x, (x * x).sum(1), y)
 
 
 def kcenter_greedy(features: np.ndarray, selected_indices, K: int):
     """_select_batch (core_set.py:17-30): m = min over already-selected of d; K times
-    {j = first argmax m; assert j not selected; m = min(m, d(., j))}.  Returns (picks, m)."""
+    {j = first argmax m; assert j not selected; m = min(m, d(., j))}.  Returns (picks, m).
+    The float64 copy of the rows and their squared norms are the same values at every step, so they are
+    formed once (the per-step arithmetic is euclidean_to's, operand for operand)."""
     sel = list(selected_indices)
-    m = euclidean_to(features, np.asarray(features)[sel]).min(axis=1)
+    x = np.asarray(features, dtype=np.float64)
+    xx = (x * x).sum(1)
+    m = _euclidean_f64(x, xx, x[sel]).min(axis=1)
     picks = []
     for _ in range(K):
         j = int(np.argmax(m))
         assert j not in sel, "k-center picked an already selected index (core_set.py:25)"
-        m = np.minimum(m, euclidean_to(features, np.asarray(features)[[j]])[:, 0])
+        m = np.minimum(m, _euclidean_f64(x, xx, x[[j]])[:, 0])
         picks.append(j)
     return picks, m
 
