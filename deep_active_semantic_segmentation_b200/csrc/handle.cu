@@ -14,6 +14,9 @@ namespace das {
 thread_local int g_last_cuda_error = 0;
 std::atomic<unsigned long long> g_launch_count{0};
 
+// DAS_OPT_MC_UP_WARPS: 4 | 15 = pixel-pair kernel, 220 = one-pixel-per-lane kernel (the variants mc_inst.cu builds)
+static bool up_warps_option_ok(int v) { return v == 4 || v == 15 || v == 220; }
+
 static int env_int(const char* name, int fallback) {
     const char* e = getenv(name);
     if (e == nullptr || e[0] == '\0') return fallback;
@@ -173,7 +176,7 @@ int das_handle_create(int device, das_handle** out) {
     }
     {
         const int v = env_int("DAS_MC_UP_WARPS", 0);
-        h->opt[DAS_OPT_MC_UP_WARPS] = (v == 4 || v == 15) ? v : 0;
+        h->opt[DAS_OPT_MC_UP_WARPS] = up_warps_option_ok(v) ? v : 0;
     }
     h->opt[DAS_OPT_GEMM_2CTA] = env_int("DAS_GEMM_2CTA", 1) != 0;
     h->opt[DAS_OPT_KC_CLUSTER] = env_int("DAS_KC_CLUSTER", 1) != 0;
@@ -213,7 +216,7 @@ int das_handle_set_option(das_handle* h, int option, int value) {
             if (value < 0 || value > 8) return DAS_ERR_INVALID_ARG;
             break;
         case DAS_OPT_MC_UP_WARPS:
-            if (value != 0 && value != 4 && value != 15) return DAS_ERR_INVALID_ARG;
+            if (value != 0 && !up_warps_option_ok(value)) return DAS_ERR_INVALID_ARG;
             break;
         default:
             value = value != 0;

@@ -279,7 +279,7 @@ static float up_scale(int n_in, int n_out) { return n_out > 1 ? (float)(n_in - 1
 // does every `tile`-pixel tile of the output axis read at most `window` consecutive source samples, and does a
 // 4-pixel strip (tile % 4 == 0) start at most one source sample after its first pixel's?  (the kernel's arithmetic,
 // replayed on the host: IEEE float multiply, truncation)
-static bool up_window_fits(int n_in, int n_out, float scale, int tile, int window) {
+static bool up_window_fits(int n_in, int n_out, float scale, int tile, int window, int strip) {
     auto src = [&](int d) {
         int i = (int)(scale * (float)d);
         return i > n_in - 1 ? n_in - 1 : i;
@@ -290,24 +290,31 @@ static bool up_window_fits(int n_in, int n_out, float scale, int tile, int windo
         const int i1 = i0 + (i0 < n_in - 1 ? 1 : 0);
         if (i1 - src(t0) > window - 1) return false;
     }
-    for (int s0 = 0; s0 < n_out; s0 += kUpStrip) {
-        const int last = (s0 + kUpStrip - 1 < n_out ? s0 + kUpStrip - 1 : n_out - 1);
+    for (int s0 = 0; s0 < n_out; s0 += strip) {
+        const int last = (s0 + strip - 1 < n_out ? s0 + strip - 1 : n_out - 1);
         if (src(last) - src(s0) > 1) return false;
     }
     return true;
 }
+// kernel variant code `nw`: 4 | 15 = pixel-pair kernel with that many consumer warps (mc_up.cuh, strips of 4 columns);
+// 200 + NW = one-pixel-per-lane kernel (mc_up1.cuh, strips of 2 columns, NW consumer warps; 220 is built)
+static bool up_is_v1(int nw) { return nw >= 100; }
+static int up_variant_tile_w(int nw) { return up_is_v1(nw) ? up1_tile_w(nw % 100) : up_tile_w(nw); }
+static int up_variant_win_cols(int nw) { return up_is_v1(nw) ? up1_win_cols(nw % 100) : up_win_cols(nw); }
+static bool up_variant_known(int nw) { return nw == 4 || nw == 15 || nw == 220; }
 static bool up_supported(int h, int w, int H, int W, int nw) {
     if (h < 1 || w < 1 || H < 1 || W < 1) return false;
-    return up_window_fits(h, H, up_scale(h, H), kUpTileH, kUpRows) &&
-           up_window_fits(w, W, up_scale(w, W), up_tile_w(nw), up_win_cols(nw));
+    return up_window_fits(h, H, up_scale(h, H), kUpTileH, kUpRows, kUpStrip) &&
+           up_window_fits(w, W, up_scale(w, W), up_variant_tile_w(nw), up_variant_win_cols(nw),
+                          up_is_v1(nw) ? kUp1Strip : kUpStrip);
 }
 // consumer warps per CTA (0 = the shape is not supported).  15 (one 512-thread CTA per SM, tile 16 x 60, one
 // producer warp per SM) measured 3-8 % faster than 4 (three 160-thread CTAs per SM, tile 16 x 16) on 512 x 1024 and
-// 513 x 513 outputs (profiles/r1_upsample_notes.md); narrow outputs keep the small tile.  DAS_OPT_MC_UP_WARPS = 4 | 15
+// 513 x 513 outputs (profiles/r1_upsample_notes.md); narrow outputs keep the small tile.  DAS_OPT_MC_UP_WARPS
 // overrides the choice.
 static int up_warps(const das_handle* hd, int h, int w, int H, int W) {
     const int v = hd != nullptr ? hd->opt[DAS_OPT_MC_UP_WARPS] : 0;
-    if (v == 4 || v == 15) return up_supported(h, w, H, W, v) ? v : 0;
+    if (v != 0 && up_variant_known(v)) return up_supported(h, w, H, W, v) ? v : 0;
     if (W >= 2 * up_tile_w(15) && up_supported(h, w, H, W, 15)) return 15;
     return up_supported(h, w, H, W, 4) ? 4 : 0;
 }
@@ -415,12 +422,14 @@ int das_mc_upsample_accumulate_finalize(das_handle* hd, const das_mc_desc* desc,
     if (pass_lowres_logits == nullptr || h < 1 || w < 1) return DAS_ERR_INVALID_ARG;
     if (n_passes < 1 || n_passes > desc->T_cap) return DAS_ERR_INVALID_ARG;
     if (n_passes > DAS_MAX_PASS_GROUP) return DAS_ERR_UNSUPPORTED;
-    const int nw = up_warps(hd, h, w, desc->H, desc->W);
+    int nw = up_warps(hd, h, w, desc->H, desc->W);
     if (nw == 0) return DAS_ERR_UNSUPPORTED;
+    // the one-pixel-per-lane kernel forms source offsets inside the whole BATCH in 32 bits
+    if (up_is_v1(nw) && (unsigned long long)desc->B * desc->C * h * w >= (1ull << 32)) return DAS_ERR_UNSUPPORTED;
     // source offsets inside one image are formed in 32 bits
     if ((unsigned long long)desc->C * h * w >= (1ull << 31)) return DAS_ERR_UNSUPPORTED;
     McUpParams q;
-    const int tiles_x = (desc->W + up_tile_w(nw) - 1) / up_tile_w(nw), tiles_y = (desc->H + kUpTileH - 1) / kUpTileH;
+    const int tiles_x = (desc->W + up_variant_tile_w(nw) - 1) / up_variant_tile_w(nw), tiles_y = (desc->H + kUpTileH - 1) / kUpTileH;
     rc = fill_fin_params(desc, state, labels, n_passes, vote_entropy, pred_entropy, bald, confidence, margin,
                          weak_labels, tiles_x * tiles_y, &q.fin);
     if (rc != DAS_OK) return rc;

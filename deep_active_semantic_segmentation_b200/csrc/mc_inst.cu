@@ -195,11 +195,43 @@ int launch_score_up_nw(const McUpParams& p, int flags, cudaStream_t st) {
     return DAS_OK;
 }
 
+// One pixel per lane, class pairs in the packed pipe (mc_up1.cuh): NW consumer warps per CTA, tile = 16 rows x 2 NW columns.
+template <int C, int NW, int NP, int MINB>
+int launch_score_up1_nw(const McUpParams& p, int flags, cudaStream_t st) {
+    const bool probs = flags & DAS_MC_PROBS, votes = flags & DAS_MC_VOTES;
+    McUpParams q = p;
+    q.stages = 4;
+    const size_t smem = up1_rows_bytes(C, NW) + up1_wts_bytes(NW) + (size_t)q.stages * up1_stage_bytes(C, NW);
+    const int tiles = p.B * p.tiles_x * p.tiles_y;
+#define DAS_UP1(P, Q)                                                                              \
+    do {                                                                                           \
+        int rc__ = set_smem(mc_score_up1_kernel<C, P, Q, NW, NP, MINB>, smem);                         \
+        if (rc__ != DAS_OK) return rc__;                                                           \
+        int occ__ = 0;                                                                             \
+        cudaError_t e__ = cudaOccupancyMaxActiveBlocksPerMultiprocessor(                           \
+            &occ__, mc_score_up1_kernel<C, P, Q, NW, NP, MINB>, 32 * (NW + NP), smem);                 \
+        if (e__ != cudaSuccess) return cuda_fail(e__);                                             \
+        if (occ__ < 1) return DAS_ERR_UNSUPPORTED;                                                 \
+        if (occ__ > MINB) occ__ = MINB;                                                            \
+        const int grid__ = tiles < q.num_sms * occ__ ? tiles : q.num_sms * occ__;                  \
+        DAS_LAUNCH((mc_score_up1_kernel<C, P, Q, NW, NP, MINB>), grid__, 32 * (NW + NP), smem, st, q); \
+    } while (0)
+    if (probs && votes) DAS_UP1(true, true);
+    else if (probs) DAS_UP1(true, false);
+    else DAS_UP1(false, true);
+#undef DAS_UP1
+    DAS_CHECK_LAUNCH();
+    return DAS_OK;
+}
+
+// nw: 4 | 15 = pixel-pair kernel (mc_up.cuh); 220 = one-pixel-per-lane kernel (mc_up1.cuh) with 20 consumer + 4 producer
+// warps - the best of the splits measured in round 2 (profiles/r2_upsample_notes.md); opt-in through DAS_OPT_MC_UP_WARPS
 template <int C>
 int launch_score_up(const McUpParams& p, int flags, int nw, cudaStream_t st) {
     switch (nw) {
         case 4: return launch_score_up_nw<C, 4, (C <= 24 ? 3 : 2)>(p, flags, st);
         case 15: return launch_score_up_nw<C, 15, 1>(p, flags, st);
+        case 220: return launch_score_up1_nw<C, 20, 4, 1>(p, flags, st);   // 20 + 4 warps, 80 registers
         default: return DAS_ERR_INVALID_ARG;
     }
 }

@@ -631,6 +631,7 @@ __global__ void __launch_bounds__(kAccThreads, MINB) mc_score_kernel(const McSco
 }  // namespace das
 #include "mc_tma.cuh"
 #include "mc_up.cuh"
+#include "mc_up1.cuh"
 namespace das {
 
 // per-class-count launchers (instantiated in mc_inst.cu for a range of C)

@@ -164,6 +164,26 @@ def test_full_size_agrees_with_interpolate_then_score():
     assert bool((b["weak_labels"][inval] == 255).all())
 
 
+ONE_PIXEL_CASES = [CASES[0], CASES[1], CASES[3], CASES[4], CASES[5], CASES[8], (1, 5, 21, 33, 33, 129, 129)]
+
+
+@pytest.mark.parametrize("B,T,C,h,w,H,W", ONE_PIXEL_CASES)
+def test_one_pixel_per_lane_variant(B, T, C, h, w, H, W):
+    """DAS_OPT_MC_UP_WARPS = 220 (csrc/mc_up1.cuh: one pixel per lane, class pairs in the packed fp32 pipe, 20 consumer +
+    4 producer warps): the oracle's results, and - because every sum keeps the association of the pixel-pair kernel -
+    bit-identical per-pixel maps (odd and even class counts, ragged tiles, two classes, the maximum class count)."""
+    ops = _ops()
+    low = synth.pool_logits(17, list(range(B)), T, C, h, w, 2)
+    labels = synth.pool_labels(17, list(range(B)), H, W, C, 8)
+    ref = run_up(low, labels, H, W, weak=True)
+    with ops.option("mc_up_warps", 220):
+        res = run_up(low, labels, H, W, weak=True)
+    check_up_against_oracle(res, low, labels, H, W)
+    for name in ("vote_entropy", "weak_labels") + PROB_MAPS:
+        np.testing.assert_array_equal(res[name], ref[name], err_msg=name)
+    np.testing.assert_allclose(res["scores"], ref["scores"], rtol=2e-6, atol=1e-7)   # other tile partition of the image sums
+
+
 def test_batching_invariance():
     """scores of an image do not depend on the batch it is scored in (fixed-order tile partials)"""
     B, T, C, h, w, H, W = 3, 4, 19, 17, 33, 65, 130
