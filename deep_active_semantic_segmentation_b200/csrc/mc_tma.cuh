@@ -51,6 +51,25 @@ __device__ __forceinline__ void tma_mbar_wait(uint32_t bar, uint32_t parity) {
         : "memory");
 }
 
+// for warps that have nothing to do until the barrier flips: poll it with a pause in between, so that the polling does not
+// take issue slots from the warps that work
+__device__ __forceinline__ void tma_mbar_wait_idle(uint32_t bar, uint32_t parity) {
+    for (;;) {
+        uint32_t done;
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t"
+            "}\n"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+        if (done) break;
+        __nanosleep(256);
+    }
+}
+
 // CTAs per SM: 3 x 160 threads at 128 registers for C <= 20, 2 x 160 at up to 200 registers for more classes.
 // (__maxnreg__(136) removes the last 16-byte spill at C = 19 but the per-warp register allocation granularity
 // then only fits 2 CTAs per SM: measured 0.85 instead of 0.96 of the HBM peak.)

@@ -259,6 +259,18 @@ __global__ void __launch_bounds__(32 * (NW + NP), MINB) mc_score_up1_kernel(cons
         float ent = 0.f;
         uint32_t first_vote = 0;
 
+        // A warp whose strip lies past the right edge of the plane (the last tile of a row: 1024 = 17 x 60 + 4) only keeps
+        // the ring moving: it waits for each stage (which also keeps it from running ahead of the barrier phases) and
+        // hands it back, leaving its issue slots to the warps that have pixels.  The flag goes through a shuffle so
+        // that the compiler sees a warp-uniform branch (the ring position stays in uniform registers).
+        if (!__shfl_sync(0xffffffffu, xs0 < q.W ? 1 : 0, 0)) {
+            for (int g = 0; g < T; ++g) {
+                tma_mbar_wait_idle(bar0 + 8u * stage, phase);
+                if (lane == 0)
+                    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar0 + 8u * (S + stage)) : "memory");
+                if (++stage == S) stage = 0, phase ^= 1u;
+            }
+        } else
         for (int g = 0; g < T; ++g) {
             // ---- phase 1: horizontal interpolation of the staged window for this warp's 2 columns ----
             tma_mbar_wait(bar0 + 8u * stage, phase);
