@@ -14,8 +14,8 @@ namespace das {
 thread_local int g_last_cuda_error = 0;
 std::atomic<unsigned long long> g_launch_count{0};
 
-// DAS_OPT_MC_UP_WARPS: 4 | 15 = pixel-pair kernel, 220 = one-pixel-per-lane kernel (the variants mc_inst.cu builds)
-static bool up_warps_option_ok(int v) { return v == 4 || v == 15 || v == 220; }
+// DAS_OPT_MC_UP_WARPS: 4 | 15 = pixel-pair kernel, 220 | 216 = one-pixel-per-lane kernel (the variants mc_inst.cu builds)
+static bool up_warps_option_ok(int v) { return v == 4 || v == 15 || v == 220 || v == 216; }
 
 static int env_int(const char* name, int fallback) {
     const char* e = getenv(name);

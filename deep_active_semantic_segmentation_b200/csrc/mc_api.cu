@@ -301,20 +301,31 @@ static bool up_window_fits(int n_in, int n_out, float scale, int tile, int windo
 static bool up_is_v1(int nw) { return nw >= 100; }
 static int up_variant_tile_w(int nw) { return up_is_v1(nw) ? up1_tile_w(nw % 100) : up_tile_w(nw); }
 static int up_variant_win_cols(int nw) { return up_is_v1(nw) ? up1_win_cols(nw % 100) : up_win_cols(nw); }
-static bool up_variant_known(int nw) { return nw == 4 || nw == 15 || nw == 220; }
+static bool up_variant_known(int nw) { return nw == 4 || nw == 15 || nw == 220 || nw == 216; }
 static bool up_supported(int h, int w, int H, int W, int nw) {
     if (h < 1 || w < 1 || H < 1 || W < 1) return false;
     return up_window_fits(h, H, up_scale(h, H), kUpTileH, kUpRows, kUpStrip) &&
            up_window_fits(w, W, up_scale(w, W), up_variant_tile_w(nw), up_variant_win_cols(nw),
                           up_is_v1(nw) ? kUp1Strip : kUpStrip);
 }
-// consumer warps per CTA (0 = the shape is not supported).  15 (one 512-thread CTA per SM, tile 16 x 60, one
-// producer warp per SM) measured 3-8 % faster than 4 (three 160-thread CTAs per SM, tile 16 x 16) on 512 x 1024 and
-// 513 x 513 outputs (profiles/r1_upsample_notes.md); narrow outputs keep the small tile.  DAS_OPT_MC_UP_WARPS
-// overrides the choice.
-static int up_warps(const das_handle* hd, int h, int w, int H, int W) {
+// Kernel variant for a shape (0 = not supported).  Measured on the B200 (profiles/r2_upsample_notes.md, 512 x 1024 and
+// 513 x 513 outputs, B = 8, T = 20):
+//   C <= 20  one pixel per lane, 20 consumer + 4 producer warps at 80 registers (220): 0.934 ms against 0.974 ms for the
+//            pixel-pair kernel at C = 19 (0.490 / 0.520 ms on the Pascal shape)
+//   C == 21  pixel pairs, 15 + 1 warps at 128 registers (15): 0.529 against 0.559 ms (Pascal shape), 1.026 / 1.072 ms
+//   C >= 22  one pixel per lane, 16 + 4 warps at 96 registers (216): the pixel-pair kernel spills from here on
+//            (C = 24: 1.17 against 1.22 ms, C = 28: 1.32 / 1.66, C = 32: 1.50 / 2.14)
+// Narrow outputs (less than two of the wide tiles per row) keep the pixel-pair kernel with three 160-thread CTAs per SM
+// and 16 x 16 tiles (4).  B and C are 0 when only the shape is asked about (das_mc_upsample_supported).
+// DAS_OPT_MC_UP_WARPS overrides the choice.
+static int up_warps(const das_handle* hd, int h, int w, int H, int W, int B = 0, int C = 0) {
     const int v = hd != nullptr ? hd->opt[DAS_OPT_MC_UP_WARPS] : 0;
     if (v != 0 && up_variant_known(v)) return up_supported(h, w, H, W, v) ? v : 0;
+    const int v1 = C == 0 || C == 21 ? 0 : (C <= 20 ? 220 : 216);
+    // the one-pixel-per-lane kernel forms source offsets inside the whole BATCH in 32 bits
+    if (v1 != 0 && W >= 2 * up_variant_tile_w(v1) && (unsigned long long)B * C * h * w < (1ull << 32) &&
+        up_supported(h, w, H, W, v1))
+        return v1;
     if (W >= 2 * up_tile_w(15) && up_supported(h, w, H, W, 15)) return 15;
     return up_supported(h, w, H, W, 4) ? 4 : 0;
 }
@@ -422,7 +433,7 @@ int das_mc_upsample_accumulate_finalize(das_handle* hd, const das_mc_desc* desc,
     if (pass_lowres_logits == nullptr || h < 1 || w < 1) return DAS_ERR_INVALID_ARG;
     if (n_passes < 1 || n_passes > desc->T_cap) return DAS_ERR_INVALID_ARG;
     if (n_passes > DAS_MAX_PASS_GROUP) return DAS_ERR_UNSUPPORTED;
-    int nw = up_warps(hd, h, w, desc->H, desc->W);
+    const int nw = up_warps(hd, h, w, desc->H, desc->W, desc->B, desc->C);
     if (nw == 0) return DAS_ERR_UNSUPPORTED;
     // the one-pixel-per-lane kernel forms source offsets inside the whole BATCH in 32 bits
     if (up_is_v1(nw) && (unsigned long long)desc->B * desc->C * h * w >= (1ull << 32)) return DAS_ERR_UNSUPPORTED;

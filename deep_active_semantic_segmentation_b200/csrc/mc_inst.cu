@@ -224,14 +224,16 @@ int launch_score_up1_nw(const McUpParams& p, int flags, cudaStream_t st) {
     return DAS_OK;
 }
 
-// nw: 4 | 15 = pixel-pair kernel (mc_up.cuh); 220 = one-pixel-per-lane kernel (mc_up1.cuh) with 20 consumer + 4 producer
-// warps - the best of the splits measured in round 2 (profiles/r2_upsample_notes.md); opt-in through DAS_OPT_MC_UP_WARPS
+// nw: 4 | 15 = pixel-pair kernel (mc_up.cuh); 220 | 216 = one-pixel-per-lane kernel (mc_up1.cuh) with 20 | 16 consumer + 4
+// producer warps - the best of the splits measured in round 2 (profiles/r2_upsample_notes.md).  mc_api.cu: up_warps()
+// picks per class count; DAS_OPT_MC_UP_WARPS forces one
 template <int C>
 int launch_score_up(const McUpParams& p, int flags, int nw, cudaStream_t st) {
     switch (nw) {
         case 4: return launch_score_up_nw<C, 4, (C <= 24 ? 3 : 2)>(p, flags, st);
         case 15: return launch_score_up_nw<C, 15, 1>(p, flags, st);
         case 220: return launch_score_up1_nw<C, 20, 4, 1>(p, flags, st);   // 20 + 4 warps, 80 registers
+        case 216: return launch_score_up1_nw<C, 16, 4, 1>(p, flags, st);   // 16 + 4 warps, 96 registers
         default: return DAS_ERR_INVALID_ARG;
     }
 }

@@ -141,6 +141,30 @@ struct Acc {
 
 constexpr size_t acc_smem_bytes(int C, int VEC) { return (size_t)C * kAccThreads * VEC * sizeof(float); }
 
+// Maximum of N floats as a 3-ary tree (depth 3 for N <= 27 instead of an N-long chain; max is exact, so the shape does
+// not change the result).  One template level per tree level: every loop has a constant trip count.  (The same tree
+// written as a loop over levels - `for (n = C; n > 1; n = (n + 2) / 3)` - is not unrolled by nvcc 12.9 for C >= 22: the
+// array then lives in LOCAL memory, 88 - 128 bytes of stack traffic per pass in every kernel.)
+template <int N>
+struct MaxTree {
+    static __device__ __forceinline__ float run(const float (&t)[N]) {
+        constexpr int M = (N + 2) / 3;
+        float u[M];
+#pragma unroll
+        for (int i = 0; i < M; ++i) {
+            float v = t[3 * i];
+            if (3 * i + 1 < N) v = fmaxf(v, t[3 * i + 1]);
+            if (3 * i + 2 < N) v = fmaxf(v, t[3 * i + 2]);
+            u[i] = v;
+        }
+        return MaxTree<M>::run(u);
+    }
+};
+template <>
+struct MaxTree<1> {
+    static __device__ __forceinline__ float run(const float (&t)[1]) { return t[0]; }
+};
+
 // One Monte-Carlo pass for the VEC pixels of a thread: loads the C logits of each pixel once (streaming, evict
 // first), returns the votes packed one byte per pixel and updates the running accumulators.
 //   vote   v   = first argmax_c x_c                                     (mc_dropout.py:40)
@@ -177,17 +201,7 @@ __device__ __forceinline__ uint32_t mc_pass_math(float (&x)[C][VEC], Acc<C, VEC,
         float t[C];
 #pragma unroll
         for (int c = 0; c < C; ++c) t[c] = x[c][j];
-#pragma unroll
-        for (int n = C; n > 1; n = (n + 2) / 3) {
-#pragma unroll
-            for (int i = 0; i < (n + 2) / 3; ++i) {
-                float v = t[3 * i];
-                if (3 * i + 1 < n) v = fmaxf(v, t[3 * i + 1]);
-                if (3 * i + 2 < n) v = fmaxf(v, t[3 * i + 2]);
-                t[i] = v;
-            }
-        }
-        m[j] = t[0];
+        m[j] = MaxTree<C>::run(t);
     }
     // d_c = x_c + (0 - m): exactly +0 for the maxima, negative otherwise (IEEE subtraction of distinct floats is never
     // 0), so the sign bits ARE the "not a maximum" flags: one funnel shift per class collects them (instead of a

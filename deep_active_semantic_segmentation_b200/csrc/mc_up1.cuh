@@ -45,17 +45,7 @@ __device__ __forceinline__ uint32_t mc_pass_math_pairs(f32x2 (&x)[(C + 1) / 2], 
         float t[C];
 #pragma unroll
         for (int c = 0; c < C; ++c) t[c] = (c & 1) ? x[c >> 1].y : x[c >> 1].x;
-#pragma unroll
-        for (int n = C; n > 1; n = (n + 2) / 3) {
-#pragma unroll
-            for (int i = 0; i < (n + 2) / 3; ++i) {
-                float v = t[3 * i];
-                if (3 * i + 1 < n) v = fmaxf(v, t[3 * i + 1]);
-                if (3 * i + 2 < n) v = fmaxf(v, t[3 * i + 2]);
-                t[i] = v;
-            }
-        }
-        m = t[0];
+        m = MaxTree<C>::run(t);
     }
     // d_c = x_c + (0 - m): +0 for the maxima (either zero), negative otherwise - see mc_pass_math
     const float nm1 = 0.f - m;

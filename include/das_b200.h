@@ -62,8 +62,9 @@ typedef struct das_handle das_handle;
 enum {
     DAS_OPT_MC_TMA = 0,        /* DAS_MC_TMA       1: TMA-ring single-shot kernel when eligible (default), 0: LDG kernel   */
     DAS_OPT_MC_TMA_CTAS = 1,   /* DAS_MC_TMA_CTAS  CTAs per SM of the TMA kernel, 0 = per class count (default)           */
-    DAS_OPT_MC_UP_WARPS = 2,   /* DAS_MC_UP_WARPS  consumer warps of the fused-upsample kernel: 0 = auto, 4 or 15;
-                                  220 = the one-pixel-per-lane variant (20 consumer + 4 producer warps)                 */
+    DAS_OPT_MC_UP_WARPS = 2,   /* DAS_MC_UP_WARPS  kernel variant of the fused upsample: 0 = by class count and width (default),
+                                  4 | 15 = pixel pairs with that many consumer warps, 220 | 216 = one pixel per lane with
+                                  20 | 16 consumer + 4 producer warps                                                    */
     DAS_OPT_GEMM_2CTA = 3,     /* DAS_GEMM_2CTA    1: CTA-pair tcgen05 distance GEMM (default), 0: one CTA per tile       */
     DAS_OPT_KC_CLUSTER = 4,    /* DAS_KC_CLUSTER   1: k-center loop inside one thread-block cluster (default), 0: chain   */
     DAS_OPT_MC_L2_PERSIST = 5, /* DAS_MC_L2_PERSIST 1: streaming accumulators pinned in L2 when they fit (default), 0: off.

@@ -460,7 +460,7 @@ def test_handle_options_and_info():
     assert info["l2_bytes"] == torch.cuda.get_device_properties(0).L2_cache_size and info["persisting_max_bytes"] <= info["l2_bytes"]
     old = _lib.set_option("mc_tma_ctas", 2)
     assert _lib.get_option("mc_tma_ctas") == 2 and _lib.set_option("mc_tma_ctas", old) == 2
-    assert lib.das_handle_set_option(h, _lib.OPTIONS["mc_up_warps"], 7) == -1                       # only 0 / 4 / 15 / 220
+    assert lib.das_handle_set_option(h, _lib.OPTIONS["mc_up_warps"], 7) == -1                       # only 0 / 4 / 15 / 220 / 216
     assert lib.das_handle_set_option(h, 99, 1) == -1
     v = ctypes.c_int()
     assert lib.das_handle_get_option(h, _lib.OPTIONS["mc_tma"], ctypes.byref(v)) == 0 and v.value in (0, 1)

@@ -1,6 +1,5 @@
-for v in 0 220; do
-  echo "== variant $v"
-  DAS_MC_UP_WARPS=$v python tools/bench_upsample.py --only-fused --steps 200 --warmup 10 2>&1 | tail -1 | cut -c1-180
-  DAS_MC_UP_WARPS=$v python tools/bench_upsample.py --only-fused --steps 200 --warmup 10 --shape pascal 2>&1 | tail -1 | cut -c1-180
-done
-timeout 300 python -m pytest tests/test_gpu_upsample.py -q -m gpu -x 2>&1 | tail -3
+timeout 900 python -m pytest tests -q -m gpu -x 2>&1 | tail -3
+python bench.py > gpurun_out/g_bench.json 2> gpurun_out/g_bench.err; echo bench rc=$?
+python tools/bench_upsample.py > gpurun_out/g_up_cs.json 2>gpurun_out/g_up.err
+python tools/bench_upsample.py --shape pascal > gpurun_out/g_up_pascal.json 2>>gpurun_out/g_up.err
+tail -c 600 gpurun_out/g_up_cs.json; tail -c 600 gpurun_out/g_up_pascal.json

@@ -26,6 +26,7 @@ def main():
     ap.add_argument("--batch", type=int, default=8)
     ap.add_argument("--mode", default="full", choices=["full", "probs", "votes"])
     ap.add_argument("--only-fused", action="store_true", help="profiling: launch nothing but the fused kernel")
+    ap.add_argument("--classes", type=int, default=0, help="override the class count of the shape")
     a = ap.parse_args()
     import torch
     import torch.nn.functional as F
@@ -35,6 +36,8 @@ def main():
         C, T, h, w, H, W = 19, 20, 128, 256, 512, 1024
     else:
         C, T, h, w, H, W = 21, 20, 129, 129, 513, 513
+    if a.classes:
+        C = a.classes
     B = a.batch
     dev = torch.device("cuda", 0)
     votes, probs = a.mode in ("full", "votes"), a.mode in ("full", "probs")
