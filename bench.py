@@ -726,23 +726,27 @@ def fused_upsample_variant(args, dev, steps=60):
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / steps
+    # csrc/mc_api.cu up_warps(): one pixel per lane for C <= 20 (40-column tiles) and C >= 22 (32-column tiles), pixel pairs at C = 21
+    one_pixel = C != 21 and W >= 2 * (40 if C <= 20 else 32)
     out = {"value": round(B / ms * 1e3, 1), "unit": UNIT, "ms_per_step": round(ms, 4), "steps": steps,
-           "kernel": "mc_score_up_kernel (fused bilinear upsample + K1 + K2)", "lowres": [h, w],
+           "kernel": ("mc_score_up1_kernel (one pixel per lane, class pairs in the packed pipe)" if one_pixel else
+                      "mc_score_up_kernel (pixel pairs)") + ": fused bilinear upsample + K1 + K2", "lowres": [h, w],
            "hbm_bytes_per_step": T * B * C * h * w * 4,
            "fullres_bytes_avoided_per_step": 2 * T * B * C * H * W * 4,
            "note": "the network no longer writes T*B*C*H*W*4 bytes of interpolated logits and the scorer no longer reads them"}
     # The kernel reads 16x fewer bytes than the resident-logits kernel (5 % of the HBM peak): its bounds are on chip.
     #   MUFU: per pixel and pass C ex2 + 1 rcp + 1 lg2, per pixel C + 1 lg2 in the finalize; 16 MUFU lanes / clk / SM
-    #   issue: 378 warp instructions per pass and pixel pair in the pass loop (cuobjdump, C = 19) + finalize, 4 / clk / SM
+    #   issue: ~10 warp instructions per logit (pass loop + producers + finalize, ncu), 4 / clk / SM
     sm_hz = float(peaks_sm_mhz()) * 1e6
     n_sm = torch.cuda.get_device_properties(dev).multi_processor_count
     px = B * H * W
     mufu_ops = px * (T * (C + 2) + (C + 1)) if probs else 0
     mufu_peak = n_sm * 16 * sm_hz
-    # 622.2 M warp instructions per launch measured by ncu at B = 8, 512 x 1024, C = 19, T = 20 (profiles/
-    # r1_fused_upsample_ncu_summary.txt; the pass loop alone is 378 SASS instructions per pass and pixel pair), scaled
-    # linearly in pixels, passes and classes
-    warp_instr = 622.24e6 * (px / (8.0 * 512 * 1024)) * (T * C) / (20.0 * 19.0)
+    # warp instructions per launch measured by ncu at B = 8, 512 x 1024, C = 19, T = 20 (profiles/
+    # r2_fused_upsample_ncu_summary.txt), scaled linearly in pixels, passes and classes: 703.8 M for the one-pixel-per-lane
+    # kernel the library picks for C <= 20 and C >= 22, 601.6 M for the pixel-pair kernel (C = 21; 338.4 M measured on
+    # the Pascal shape = the same 0.38 per pixel, pass and class)
+    warp_instr = (703.80e6 if one_pixel else 601.57e6) * (px / (8.0 * 512 * 1024)) * (T * C) / (20.0 * 19.0)
     issue_peak = n_sm * 4 * sm_hz
     out["roofline"] = {"bound": "mufu", "algorithmic_ops": int(mufu_ops), "peak_ops_per_s": mufu_peak,
                        "achieved_ops_per_s": round(mufu_ops / (ms * 1e-3), 1), "frac": round(mufu_ops / (ms * 1e-3) / mufu_peak, 4),
