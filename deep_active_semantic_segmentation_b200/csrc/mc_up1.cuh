@@ -4,14 +4,18 @@
 // in flight = 128 registers, i.e. 4 warps per scheduler, and the kernel sits at 0.52 of its issue bound because three
 // pipes (issue, FMA, XU) are all within 20 % of each other and four warps cannot keep them overlapped
 // (profiles/r2_upsample_notes.md).  Here a lane owns ONE pixel and the packed instructions pair classes (2k, 2k+1) of that
-// pixel instead: the same number of issue slots per pixel, half the registers per thread, twice the warps per
-// scheduler.  Moving the accumulators to shared memory (round 2, measured, +19 %) bought the same occupancy with 38 more
-// LDS/STS per pass in an MIO queue that was already throttling; this form adds none.
+// pixel instead: the same number of issue slots per pixel, half the registers per thread, more warps per scheduler.
+// Moving the accumulators to shared memory (round 2, measured, +19 %) bought the same occupancy with 38 more LDS/STS per
+// pass in an MIO queue that was already throttling; this form adds none.  Measured (profiles/r2_upsample_notes.md): issue
+// slots 66 % busy instead of 56 % for 17 % more instructions - faster for C <= 20 (20 consumer warps, 80 registers) and for
+// C >= 22, where the pixel-pair kernel spills (16 consumer warps, 96 registers); mc_api.cu: up_warps() chooses.
 //
 //   tile      16 output rows x 2 NW columns per CTA; consumer warp -> 16 x 2 strip, lane -> pixel (row lane / 2, column
 //             lane % 2)
-//   producer  as in mc_up.cuh (4-byte cp.async into a ring, mbarrier per stage), but the window is stored with the two
-//             classes of a pair interleaved: [pair][6 rows][WS columns][2], so that ...
+//   producer  NP warps (4: ONE producer warp starves 20+ consumers - a third of all stall samples sat on the full-barrier
+//             wait, 1.65 instead of 1.0 ms), classes dealt round robin; 4-byte cp.async into a ring with an mbarrier per
+//             stage as in mc_up.cuh, but the window is stored with the two classes of a pair interleaved:
+//             [pair][6 rows][WS columns][2], so that ...
 //   phase 1   ... one lane per (class pair, source row) item reads the 3 window columns of both classes with 3 LDS.64,
 //             interpolates the strip's 2 pixels HORIZONTALLY in the 3-weight form of mc_up.cuh with the pair in the two
 //             halves of FFMA2 / FMUL2, and writes {px0.c0, px0.c1, px1.c0, px1.c1} with one STS.128 into
