@@ -727,7 +727,7 @@ def fused_upsample_variant(args, dev, steps=60):
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / steps
     # csrc/mc_api.cu up_warps(): one pixel per lane for C <= 20 (40-column tiles) and C >= 22 (32-column tiles), pixel pairs at C = 21
-    one_pixel = C != 21 and W >= 2 * (40 if C <= 20 else 32)
+    one_pixel = probs and C != 21 and W >= 2 * (40 if C <= 20 else 32)
     out = {"value": round(B / ms * 1e3, 1), "unit": UNIT, "ms_per_step": round(ms, 4), "steps": steps,
            "kernel": ("mc_score_up1_kernel (one pixel per lane, class pairs in the packed pipe)" if one_pixel else
                       "mc_score_up_kernel (pixel pairs)") + ": fused bilinear upsample + K1 + K2", "lowres": [h, w],

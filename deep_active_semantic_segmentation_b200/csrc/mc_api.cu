@@ -317,11 +317,14 @@ static bool up_supported(int h, int w, int H, int W, int nw) {
 //            (C = 24: 1.17 against 1.22 ms, C = 28: 1.32 / 1.66, C = 32: 1.50 / 2.14)
 // Narrow outputs (less than two of the wide tiles per row) keep the pixel-pair kernel with three 160-thread CTAs per SM
 // and 16 x 16 tiles (4).  B and C are 0 when only the shape is asked about (das_mc_upsample_supported).
+// Vote-only scoring (no softmax, no accumulators: nothing to gain from fewer registers) stays with the pixel-pair kernel:
+// 0.788 against 0.838 ms at C = 19, 0.996 / 1.023 at C = 24 (its producer, fully unrolled, is no longer the critical path:
+// rolled, vote-only scoring took 0.976 ms - as long as the full pass).
 // DAS_OPT_MC_UP_WARPS overrides the choice.
-static int up_warps(const das_handle* hd, int h, int w, int H, int W, int B = 0, int C = 0) {
+static int up_warps(const das_handle* hd, int h, int w, int H, int W, int B = 0, int C = 0, int flags = DAS_MC_PROBS) {
     const int v = hd != nullptr ? hd->opt[DAS_OPT_MC_UP_WARPS] : 0;
     if (v != 0 && up_variant_known(v)) return up_supported(h, w, H, W, v) ? v : 0;
-    const int v1 = C == 0 || C == 21 ? 0 : (C <= 20 ? 220 : 216);
+    const int v1 = C == 0 || C == 21 || !(flags & DAS_MC_PROBS) ? 0 : (C <= 20 ? 220 : 216);
     // the one-pixel-per-lane kernel forms source offsets inside the whole BATCH in 32 bits
     if (v1 != 0 && W >= 2 * up_variant_tile_w(v1) && (unsigned long long)B * C * h * w < (1ull << 32) &&
         up_supported(h, w, H, W, v1))
@@ -433,7 +436,7 @@ int das_mc_upsample_accumulate_finalize(das_handle* hd, const das_mc_desc* desc,
     if (pass_lowres_logits == nullptr || h < 1 || w < 1) return DAS_ERR_INVALID_ARG;
     if (n_passes < 1 || n_passes > desc->T_cap) return DAS_ERR_INVALID_ARG;
     if (n_passes > DAS_MAX_PASS_GROUP) return DAS_ERR_UNSUPPORTED;
-    const int nw = up_warps(hd, h, w, desc->H, desc->W, desc->B, desc->C);
+    const int nw = up_warps(hd, h, w, desc->H, desc->W, desc->B, desc->C, desc->flags);
     if (nw == 0) return DAS_ERR_UNSUPPORTED;
     // the one-pixel-per-lane kernel forms source offsets inside the whole BATCH in 32 bits
     if (up_is_v1(nw) && (unsigned long long)desc->B * desc->C * h * w >= (1ull << 32)) return DAS_ERR_UNSUPPORTED;

@@ -122,17 +122,24 @@ __global__ void __launch_bounds__(32 * (NW + 1), MINB) mc_score_up_kernel(const 
             }
             for (int g = 0; g < T; ++g) {
                 tma_mbar_wait(bar0 + 8u * (S + stage), phase ^ 1u);
+                // The class loop is fully unrolled: the shared-memory offsets of a class are immediates and a copy costs one
+                // 64-bit multiply-add for its address + the cp.async.  Rolled (24 instructions per class, 456 per pass from
+                // ONE warp that gets a quarter of its scheduler) the producer was the critical path of the whole kernel:
+                // votes-only scoring took as long as the full pass (profiles/r2_upsample_notes.md).
                 const float* src = q.lowres[g] + (size_t)b * C * plane;
-                uint32_t dst = ring0 + stage * kStageBytes;
-#pragma unroll 1
+                uint32_t plane_g = (uint32_t)plane;
+                asm volatile("" : "+r"(plane_g));  // per-pass value: keeps C x SLOT_ITERS hoisted offsets out of the registers
+                uint32_t dst[SLOT_ITERS];
+#pragma unroll
+                for (int j = 0; j < SLOT_ITERS; ++j) dst[j] = ring0 + stage * kStageBytes + soff[j] * 4u;
+#pragma unroll
                 for (int c = 0; c < C; ++c) {
 #pragma unroll
                     for (int j = 0; j < SLOT_ITERS; ++j)
-                        if (lane + 32 * j < kSlots)
-                            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst + soff[j] * 4u), "l"(src + goff[j])
+                        if (lane + 32 * j < kSlots)  // element offsets inside an image fit 32 bits (host check)
+                            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst[j] + (uint32_t)(c * kUpRows * WS * 4)),
+                                         "l"(src + (goff[j] + (uint32_t)c * plane_g))
                                          : "memory");
-                    src += plane;
-                    dst += kUpRows * WS * 4u;
                 }
                 // the lane's arrival fires when all of its copies above have landed
                 asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar0 + 8u * stage) : "memory");
