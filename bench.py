@@ -726,11 +726,13 @@ def fused_upsample_variant(args, dev, steps=60):
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / steps
-    # csrc/mc_api.cu up_warps(): one pixel per lane for C <= 20 (40-column tiles) and C >= 22 (32-column tiles), pixel pairs at C = 21
-    one_pixel = probs and C != 21 and W >= 2 * (40 if C <= 20 else 32)
+    # which kernel the library launches for this shape (csrc/mc_api.cu up_warps(): one pixel per lane for C <= 20 and
+    # C >= 22, pixel pairs at C = 21 and for vote-only scoring)
+    variant = ops.upsample_variant(B, C, h, w, H, W, votes=votes, probs=probs, device=dev)
+    one_pixel = variant >= 100
     out = {"value": round(B / ms * 1e3, 1), "unit": UNIT, "ms_per_step": round(ms, 4), "steps": steps,
            "kernel": ("mc_score_up1_kernel (one pixel per lane, class pairs in the packed pipe)" if one_pixel else
-                      "mc_score_up_kernel (pixel pairs)") + ": fused bilinear upsample + K1 + K2", "lowres": [h, w],
+                      "mc_score_up_kernel (pixel pairs)") + ": fused bilinear upsample + K1 + K2", "variant": variant, "lowres": [h, w],
            "hbm_bytes_per_step": T * B * C * h * w * 4,
            "fullres_bytes_avoided_per_step": 2 * T * B * C * H * W * 4,
            "note": "the network no longer writes T*B*C*H*W*4 bytes of interpolated logits and the scorer no longer reads them"}

@@ -59,6 +59,7 @@ _PROTOTYPES = {
     "das_mc_upsample_accumulate_finalize": (_i, [_h, C.POINTER(McDesc), _vp, C.POINTER(_vp), _i, _i, _i, _vp, _vp,
                                                   _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "das_mc_upsample_supported": (_i, [_h, _i, _i, _i, _i]),
+    "das_mc_upsample_variant": (_i, [_h, C.POINTER(McDesc), _i, _i]),
     "das_mc_votes_ptr": (_i, [C.POINTER(McDesc), _vp, C.POINTER(_vp)]),
     "das_suppress_rects": (_i, [_h, _vp, _i, _i, _i, _vp, _i, _vp]),
     "das_suppress_rects_host": (_i, [_h, _vp, _i, _i, _i, C.POINTER(C.c_int32), _i, _vp]),

@@ -425,6 +425,14 @@ int das_mc_upsample_supported(const das_handle* hd, int h, int w, int H, int W) 
     return up_warps(hd, h, w, H, W) != 0 ? 1 : 0;  // hd == NULL: the default options (host-only question)
 }
 
+int das_mc_upsample_variant(const das_handle* hd, const das_mc_desc* desc, int h, int w) {
+    if ((hd != nullptr && hd->magic != kDasHandleMagic) || desc == nullptr) return 0;
+    if (mc_validate(desc) != DAS_OK || (unsigned long long)desc->C * h * w >= (1ull << 31)) return 0;
+    const int nw = up_warps(hd, h, w, desc->H, desc->W, desc->B, desc->C, desc->flags);
+    if (up_is_v1(nw) && (unsigned long long)desc->B * desc->C * h * w >= (1ull << 32)) return 0;  // forced by the option
+    return nw;
+}
+
 int das_mc_upsample_accumulate_finalize(das_handle* hd, const das_mc_desc* desc, void* state,
                                         const float* const* pass_lowres_logits, int n_passes, int h, int w,
                                         const float* labels, float* vote_entropy, float* pred_entropy, float* bald,

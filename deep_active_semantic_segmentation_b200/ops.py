@@ -204,6 +204,18 @@ def upsample_supported(h: int, w: int, H: int, W: int, device=None) -> bool:
     return bool(_lib.load().das_mc_upsample_supported(_h(device), int(h), int(w), int(H), int(W)))
 
 
+def upsample_variant(B: int, C: int, h: int, w: int, H: int, W: int, votes: bool = True, probs: bool = True,
+                     device=None, default_options: bool = False) -> int:
+    """Which fused-upsample kernel score_upsampled() would launch (das_mc_upsample_variant, host only): 0 = shape not
+    supported, 4 / 15 = pixel pairs per lane, 220 / 216 = one pixel per lane (include/das_b200.h).
+    `default_options=True` asks with a NULL handle (no CUDA context needed)."""
+    flags = (MC_VOTES if votes else 0) | (MC_PROBS if probs else 0) | MC_SINGLE_SHOT
+    desc = McDesc(int(B), int(C), int(H), int(W), 1, flags)
+    hd = None if default_options else _h(device)
+    import ctypes   # the module alias `C` is shadowed by the class count here
+    return int(_lib.load().das_mc_upsample_variant(hd, ctypes.byref(desc), int(h), int(w)))
+
+
 # ---------------------------------------------------------------------------------------------
 # region path
 # ---------------------------------------------------------------------------------------------

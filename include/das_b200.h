@@ -194,6 +194,10 @@ int das_mc_upsample_accumulate_finalize(das_handle* hd, const das_mc_desc* desc,
 /* 1 if das_mc_upsample_accumulate_finalize handles the h x w -> H x W interpolation, else 0 (host only; hd may be NULL:
  * the default options are assumed). */
 int das_mc_upsample_supported(const das_handle* hd, int h, int w, int H, int W);
+/* Which kernel das_mc_upsample_accumulate_finalize would launch for `desc` (B, C, H, W, flags) and an h x w source
+ * (host only; hd may be NULL: the default options): 0 = unsupported shape, 4 | 15 = pixel pairs per lane with that many
+ * consumer warps, 220 | 216 = one pixel per lane with 20 | 16 consumer + 4 producer warps (DAS_OPT_MC_UP_WARPS). */
+int das_mc_upsample_variant(const das_handle* hd, const das_mc_desc* desc, int h, int w);
 
 /* Device pointer to the recorded votes, u8 [B,T_cap,H,W] (test / debugging aid). */
 int das_mc_votes_ptr(const das_mc_desc* desc, void* state, uint8_t** votes);

@@ -231,6 +231,25 @@ def test_upsample_shape_support_is_decided_on_the_host():
     assert ok(1, 1, 16, 16) and ok(5, 5, 16, 16)
 
 
+def test_upsample_kernel_variant_is_chosen_by_class_count_width_and_flags():
+    """das_mc_upsample_variant (host only): the measured choice of csrc/mc_api.cu up_warps() - one pixel per lane with 20 + 4
+    warps up to 20 classes, pixel pairs at 21, one pixel per lane with 16 + 4 warps from 22 on (the pixel-pair kernel
+    spills there); vote-only scoring and narrow outputs stay with the pixel-pair kernels; unsupported factors give 0."""
+    from deep_active_semantic_segmentation_b200 import ops
+    v = lambda B, C, h, w, H, W, **kw: ops.upsample_variant(B, C, h, w, H, W, default_options=True, **kw)
+    assert v(8, 19, 128, 256, 512, 1024) == 220 and v(8, 20, 129, 129, 513, 513) == 220 and v(8, 2, 128, 256, 512, 1024) == 220
+    assert v(8, 21, 129, 129, 513, 513) == 15 and v(8, 21, 128, 256, 512, 1024) == 15
+    assert v(8, 22, 128, 256, 512, 1024) == 216 and v(4, 32, 129, 129, 513, 513) == 216
+    assert v(8, 19, 128, 256, 512, 1024, probs=False) == 15 and v(8, 32, 128, 256, 512, 1024, probs=False) == 15
+    assert v(8, 19, 128, 256, 512, 1024, votes=False) == 220
+    assert v(2, 19, 12, 16, 48, 64) == 4 and v(2, 21, 17, 17, 65, 65) == 4 and v(2, 24, 5, 5, 16, 16) == 4   # narrow outputs
+    assert v(2, 19, 17, 20, 65, 80) == 220 and v(2, 19, 17, 20, 65, 79) == 4     # two 40-column tiles per row or not
+    assert v(2, 24, 17, 17, 65, 64) == 216                                       # 32-column tiles from 22 classes on
+    assert v(2, 19, 32, 32, 64, 64) == 0 and v(2, 40, 128, 256, 512, 1024) == 0 and v(0, 19, 128, 256, 512, 1024) == 0
+    # source offsets of the whole batch must fit 32 bits in the one-pixel kernel: 2^32 / (19 * 128 * 256) = 6898.3 images
+    assert v(6898, 19, 128, 256, 512, 1024) == 220 and v(6899, 19, 128, 256, 512, 1024) == 15
+
+
 def test_align_corners_axis_of_the_oracle():
     from oracle import restate as R
     for n_in, n_out in ((128, 512), (129, 513), (256, 1024), (5, 16), (1, 7), (9, 9)):
